@@ -1,0 +1,173 @@
+/*
+ * nohuman_gpu.h — C ABI of libnohuman_gpu.so, the B200 (sm_100a) replacement
+ * for the one hot path of mbhall88/nohuman: the kraken2 classification that
+ * the reference runs as a child process.
+ *
+ * What each entry point replaces in the reference (/root/reference):
+ *   - the whole group stands where `CommandRunner::run` spawns kraken2:
+ *       src/lib.rs:22-23    Command::new("kraken2").args(args).output()
+ *       src/main.rs:270     kraken.run(&kraken_cmd)
+ *   - nh_db_open            <- `--db <dir>` (src/main.rs:212-219) after
+ *                              validate_db_directory (src/lib.rs:119-141): the
+ *                              three files hash.k2d / opts.k2d / taxo.k2d are
+ *                              read unchanged
+ *   - nh_params_t           <- `--confidence` (src/main.rs:213,222-223; parsed
+ *                              by parse_confidence_score, src/lib.rs:145-151),
+ *                              `--paired` (src/main.rs:230-235),
+ *                              `--classified-out|--unclassified-out`
+ *                              (src/main.rs:259-265), `--threads`
+ *                              (src/main.rs:212,216-217); minimum_hit_groups is
+ *                              the kraken2 wrapper default (2) that nohuman
+ *                              never overrides
+ *   - nh_run_stats_t        <- the three stderr counts parsed by
+ *                              parse_kraken_stderr (src/lib.rs:61-97)
+ *   - nh_classify_batch*    <- kraken2's per-read work (upstream classify.cc
+ *                              ClassifySequence/ResolveTree)
+ *
+ * Conventions: C linkage, plain pointers and sizes, no C++/torch types, no
+ * exceptions across the boundary.  Every function returns 0 on success or a
+ * negative nh_status; nh_last_error() gives the message for the calling
+ * thread.  nh_db is immutable after open and may be shared; one nh_session
+ * per calling thread.  There is no CPU fallback: without a CUDA device every
+ * compute entry point fails with NH_ERR_CUDA.
+ */
+#ifndef NOHUMAN_GPU_H
+#define NOHUMAN_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NH_ABI_VERSION 1
+
+typedef enum {
+  NH_OK = 0,
+  NH_ERR_INVALID = -1,     /* bad argument */
+  NH_ERR_IO = -2,          /* cannot read / malformed k2d file */
+  NH_ERR_CUDA = -3,        /* CUDA runtime error or no device */
+  NH_ERR_UNSUPPORTED = -4, /* database parameters outside the kernels' range */
+  NH_ERR_CAPACITY = -5,    /* batch larger than the session was created for */
+  NH_ERR_NOMEM = -6
+} nh_status;
+
+typedef struct nh_db nh_db;
+typedef struct nh_session nh_session;
+
+/* Parameters read from opts.k2d / hash.k2d / taxo.k2d. */
+typedef struct {
+  uint64_t k, l, spaced_seed_mask, toggle_mask, minimum_acceptable_hash_value;
+  int32_t dna_db, revcom_version;
+  uint64_t capacity, size, key_bits, value_bits;
+  uint64_t node_count;
+  int32_t device;
+  int32_t reserved;
+} nh_db_info_t;
+
+typedef struct {
+  double confidence;          /* --confidence as kraken2 parses it (a double) */
+  int32_t minimum_hit_groups; /* kraken2 default 2; <0 selects the default */
+  int32_t paired;             /* sequences 2i, 2i+1 are the mates of unit i */
+  int32_t keep_human;         /* 0: keep unclassified (default nohuman), 1: keep classified (-H) */
+  int32_t threads;            /* host threads for the file API; <=0: 1 */
+  uint64_t max_batch_bases;   /* session capacity; 0 selects 256 MiB */
+  uint64_t max_batch_seqs;    /* session capacity; 0 selects max_batch_bases/64 */
+} nh_params_t;
+
+typedef struct {
+  uint64_t n_units;        /* reads (single) or pairs (paired) */
+  uint64_t n_classified;   /* kraken2 "sequences classified" */
+  uint64_t n_unclassified; /* kraken2 "sequences unclassified" */
+  uint64_t n_kept;
+  uint64_t n_bases;
+  uint64_t n_tiles;        /* minimizer-kernel work items */
+  uint64_t n_lookups;      /* hash-table probes issued */
+  float ms_plan, ms_minimizer, ms_probe, ms_score; /* device time per stage (CUDA events) */
+  float ms_h2d, ms_d2h;
+  uint32_t gpu_launches;   /* kernels launched for this batch */
+  uint32_t reserved;
+} nh_batch_stats_t;
+
+typedef struct {
+  uint64_t total;        /* "N sequences ... processed" */
+  uint64_t classified;   /* "N sequences classified" */
+  uint64_t unclassified; /* "N sequences unclassified" */
+  uint64_t bases;
+  double seconds;
+} nh_run_stats_t;
+
+/* ------------------------------------------------------------------ */
+int nh_abi_version(void);
+const char *nh_last_error(void);
+/* Number of CUDA devices visible (0 if none / no driver). */
+int nh_device_count(void);
+
+/* Open <db_dir>/{hash,opts,taxo}.k2d (or <db_dir>/db/..., as
+ * validate_db_directory does, src/lib.rs:119-141) and make the table
+ * resident in HBM of `device`. */
+int nh_db_open(const char *db_dir, int device, nh_db **out);
+/* Same, from memory images of the three files.  `cells` points at the
+ * capacity x uint32 cell array (hash.k2d after its 32-byte header); if
+ * cells_on_device != 0 it is a device pointer on `device` that the library
+ * adopts WITHOUT copying or freeing (used when one rank loads the table and
+ * NCCL-broadcasts it to the others). */
+int nh_db_open_memory(const void *opts, size_t opts_len, const void *taxo, size_t taxo_len,
+                      const uint64_t hash_header[4], const uint32_t *cells, int cells_on_device,
+                      int device, nh_db **out);
+int nh_db_info(const nh_db *db, nh_db_info_t *out);
+/* Device pointer of the resident cell array (for NCCL broadcast by the host). */
+const uint32_t *nh_db_device_cells(const nh_db *db);
+void nh_db_close(nh_db *db);
+
+int nh_session_create(nh_db *db, const nh_params_t *params, nh_session **out);
+void nh_session_destroy(nh_session *s);
+
+/* Classify one batch held in HOST memory.  bases: concatenated ASCII
+ * sequences; offsets[n_seqs+1] byte offsets.  Outputs are per unit and may be
+ * NULL: out_call = external taxid of the call (0 = unclassified, i.e.
+ * non-human for nohuman), out_keep = 1 if the unit is written to the output
+ * under params.keep_human.  H2D and D2H copies happen inside the call. */
+int nh_classify_batch(nh_session *s, const uint8_t *bases, const uint64_t *offsets,
+                      uint64_t n_seqs, uint32_t *out_call, uint8_t *out_keep,
+                      nh_batch_stats_t *stats);
+
+/* Same with DEVICE-resident input and output (all pointers are device
+ * pointers on the session's device; d_bases must be readable up to the next
+ * 16-byte boundary past total_bases).  Asynchronous on the session stream;
+ * call nh_session_sync before reading outputs or stats. */
+int nh_classify_batch_device(nh_session *s, const uint8_t *d_bases, const uint64_t *d_offsets,
+                             uint64_t n_seqs, uint64_t total_bases, uint32_t *d_out_call,
+                             uint8_t *d_out_keep);
+int nh_session_sync(nh_session *s, nh_batch_stats_t *stats);
+/* The CUDA stream (cudaStream_t) the session launches on. */
+void *nh_session_stream(nh_session *s);
+
+/* Pinned host memory for callers that want true async copies. */
+void *nh_host_alloc(size_t bytes);
+void nh_host_free(void *p);
+
+/* ---- per-stage entry points (parity tests call these through the ABI) ---- */
+/* Every k-mer position of every sequence: out_min[pos_offsets[i]+p] and
+ * out_ambig[...] as MinimizerScanner::NextMinimizer/is_ambiguous return them.
+ * pos_offsets[n_seqs+1] = exclusive scan of max(0, len-k+1). Host pointers. */
+int nh_debug_minimizers(nh_session *s, const uint8_t *bases, const uint64_t *offsets,
+                        uint64_t n_seqs, const uint64_t *pos_offsets, uint64_t *out_min,
+                        uint8_t *out_ambig);
+/* CompactHashTable::Get for n host keys -> internal taxids. */
+int nh_debug_probe(nh_session *s, const uint64_t *keys, uint64_t n, uint32_t *out_taxon);
+/* After nh_classify_batch: per-unit internal call, total_kmers, hit_groups. */
+int nh_debug_last_batch(nh_session *s, uint32_t *out_call_internal, uint32_t *out_total_kmers,
+                        uint32_t *out_hit_groups, uint64_t n_units);
+
+/* ---- roofline helper ---- */
+/* Uniformly random aligned 32-byte sector reads over the resident table:
+ * n_reads sectors per launch, `iters` launches; returns the best launch in
+ * GB/s of sectors (the random-access HBM roofline the probe is held to). */
+int nh_bench_random_gather(nh_db *db, uint64_t n_reads, int iters, double *out_gbs);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,186 @@
+"""Host-side face of the hot path, mirroring how the reference drives kraken2.
+
+The reference (mbhall88/nohuman) assembles a kraken2 argv and blocks on the
+child process (src/main.rs:210-270, src/lib.rs:22-48).  `Database` is its
+`--db` (validated like src/lib.rs:119-141), `Session` carries `--confidence`,
+`--paired` and the classified/unclassified-out polarity (src/main.rs:259-265),
+and `Session.classify` is the work kraken2 does per batch of reads.  All
+computation happens in libnohuman_gpu.so (CUDA, sm_100a).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _ffi
+from ._ffi import BatchStats, DbInfo, NhError, Params, check, lib
+
+
+def parse_confidence_score(text: str) -> float:
+    """parse_confidence_score (src/lib.rs:145-151) plus the f32 -> string ->
+    double round trip of src/main.rs:213: nohuman parses the value as f32,
+    hands kraken2 its shortest decimal form, and kraken2 re-parses a double."""
+    try:
+        f32 = np.float32(float(text))
+    except ValueError as e:  # same wording as the reference's error
+        raise ValueError("Confidence score must be a number") from e
+    if not (0.0 <= float(f32) <= 1.0):
+        raise ValueError("Confidence score must be between 0 and 1")
+    return float(np.format_float_positional(f32, unique=True, trim="0"))
+
+
+class Database:
+    """A kraken2 database (hash.k2d / opts.k2d / taxo.k2d) resident in HBM."""
+
+    def __init__(self, handle: int):
+        self._h = C.c_void_p(handle)
+
+    @classmethod
+    def open(cls, db_dir: str, device: int = 0) -> "Database":
+        h = C.c_void_p()
+        check(lib().nh_db_open(str(db_dir).encode(), device, C.byref(h)))
+        return cls(h.value)
+
+    @classmethod
+    def from_memory(cls, opts: bytes, taxo: bytes, hash_header, cells, device: int = 0,
+                    cells_on_device: bool = False) -> "Database":
+        """cells: numpy uint32 array (host) or an int device pointer."""
+        hdr = (C.c_uint64 * 4)(*[int(x) for x in hash_header])
+        h = C.c_void_p()
+        keep = None
+        if cells_on_device:
+            ptr = C.c_void_p(int(cells))
+        else:
+            keep = np.ascontiguousarray(cells, dtype=np.uint32)
+            ptr = C.c_void_p(keep.ctypes.data)
+        check(lib().nh_db_open_memory(opts, len(opts), taxo, len(taxo), hdr, ptr,
+                                      int(cells_on_device), device, C.byref(h)))
+        return cls(h.value)
+
+    @property
+    def info(self) -> DbInfo:
+        out = DbInfo()
+        check(lib().nh_db_info(self._h, C.byref(out)))
+        return out
+
+    def device_cells_ptr(self) -> int:
+        return int(lib().nh_db_device_cells(self._h) or 0)
+
+    def random_gather_gbs(self, n_reads: int = 1 << 26, iters: int = 3) -> float:
+        out = C.c_double()
+        check(lib().nh_bench_random_gather(self._h, n_reads, iters, C.byref(out)))
+        return out.value
+
+    def close(self) -> None:
+        if self._h:
+            lib().nh_db_close(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+
+class Session:
+    """One classification stream: parameters + device buffers + CUDA stream."""
+
+    def __init__(self, db: Database, confidence: float = 0.0, paired: bool = False,
+                 keep_human: bool = False, minimum_hit_groups: int = 2, threads: int = 1,
+                 max_batch_bases: int = 0, max_batch_seqs: int = 0):
+        p = Params()
+        p.confidence = float(confidence)
+        p.minimum_hit_groups = int(minimum_hit_groups)
+        p.paired = int(paired)
+        p.keep_human = int(keep_human)
+        p.threads = int(threads)
+        p.max_batch_bases = int(max_batch_bases)
+        p.max_batch_seqs = int(max_batch_seqs)
+        self.paired = bool(paired)
+        self.db = db
+        self._h = C.c_void_p()
+        check(lib().nh_session_create(db._h, C.byref(p), C.byref(self._h)))
+
+    # -- host buffers in, host results out (H2D/D2H inside the call) --
+    def classify(self, bases: np.ndarray, offsets: np.ndarray, out_call: np.ndarray | None = None,
+                 out_keep: np.ndarray | None = None):
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        n_seqs = len(offsets) - 1
+        n_units = n_seqs // 2 if self.paired else n_seqs
+        call = out_call if out_call is not None else np.empty(n_units, np.uint32)
+        keep = out_keep if out_keep is not None else np.empty(n_units, np.uint8)
+        st = BatchStats()
+        check(lib().nh_classify_batch(self._h, bases.ctypes.data, offsets.ctypes.data, n_seqs,
+                                      call.ctypes.data, keep.ctypes.data, C.byref(st)))
+        return call, keep, st
+
+    def classify_raw(self, bases_ptr: int, offsets_ptr: int, n_seqs: int, call_ptr: int,
+                     keep_ptr: int) -> BatchStats:
+        """Same call on raw host addresses (e.g. pinned torch tensors)."""
+        st = BatchStats()
+        check(lib().nh_classify_batch(self._h, bases_ptr, offsets_ptr, n_seqs, call_ptr, keep_ptr,
+                                      C.byref(st)))
+        return st
+
+    # -- device-resident (asynchronous on the session stream) ---------
+    def classify_device(self, d_bases: int, d_offsets: int, n_seqs: int, total_bases: int,
+                        d_out_call: int, d_out_keep: int) -> None:
+        check(lib().nh_classify_batch_device(self._h, d_bases, d_offsets, n_seqs, total_bases,
+                                             d_out_call, d_out_keep))
+
+    def sync(self) -> BatchStats:
+        st = BatchStats()
+        check(lib().nh_session_sync(self._h, C.byref(st)))
+        return st
+
+    @property
+    def stream(self) -> int:
+        return int(lib().nh_session_stream(self._h) or 0)
+
+    # -- per-stage entry points used by the parity tests --------------
+    def debug_minimizers(self, bases: np.ndarray, offsets: np.ndarray):
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        n_seqs = len(offsets) - 1
+        k = int(self.db.info.k)
+        lens = np.diff(offsets).astype(np.int64)
+        npos = np.maximum(lens - k + 1, 0).astype(np.uint64)
+        pos_off = np.zeros(n_seqs + 1, np.uint64)
+        np.cumsum(npos, out=pos_off[1:])
+        total = int(pos_off[-1])
+        mins = np.zeros(total + 1, np.uint64)
+        amb = np.zeros(total + 1, np.uint8)
+        check(lib().nh_debug_minimizers(self._h, bases.ctypes.data, offsets.ctypes.data, n_seqs,
+                                        pos_off.ctypes.data, mins.ctypes.data, amb.ctypes.data))
+        return mins[:total], amb[:total], pos_off
+
+    def debug_probe(self, keys: np.ndarray) -> np.ndarray:
+        keys = np.ascontiguousarray(keys, dtype=np.uint64)
+        out = np.zeros(len(keys), np.uint32)
+        check(lib().nh_debug_probe(self._h, keys.ctypes.data, len(keys), out.ctypes.data))
+        return out
+
+    def debug_last_batch(self, n_units: int):
+        call = np.zeros(n_units, np.uint32)
+        tk = np.zeros(n_units, np.uint32)
+        hg = np.zeros(n_units, np.uint32)
+        check(lib().nh_debug_last_batch(self._h, call.ctypes.data, tk.ctypes.data, hg.ctypes.data,
+                                        n_units))
+        return call, tk, hg
+
+    def close(self) -> None:
+        if self._h:
+            lib().nh_session_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+
+__all__ = ["Database", "Session", "NhError", "BatchStats", "DbInfo", "parse_confidence_score"]

@@ -1,0 +1,738 @@
+/*
+ * nh_capi.cu — the extern "C" boundary of libnohuman_gpu.so (include/nohuman_gpu.h).
+ * Host-side plumbing only: reads hash.k2d / opts.k2d / taxo.k2d unchanged
+ * (formats: SURVEY.md Appendix B), keeps the table resident in HBM, owns the
+ * per-session device buffers and stream, and sequences the four kernels of
+ * nh_kernels.cu.  No CPU classification path exists here.
+ */
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/stat.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/nohuman_gpu.h"
+#include "nh_internal.h"
+#include "nh_kernels.cuh"
+
+/* ------------------------------------------------------------------ */
+static thread_local char g_err[1024] = "";
+
+int nh_set_error(int code, const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof g_err, fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                     \
+  do {                                                                                     \
+    cudaError_t _e = (expr);                                                               \
+    if (_e != cudaSuccess)                                                                 \
+      return nh_set_error(NH_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                          __FILE__, __LINE__);                                             \
+  } while (0)
+
+extern "C" int nh_abi_version(void) { return NH_ABI_VERSION; }
+extern "C" const char *nh_last_error(void) { return g_err; }
+
+extern "C" int nh_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+/* ------------------------------------------------------------------ */
+/* database                                                            */
+
+static int read_file(const std::string &path, std::vector<uint8_t> &out, size_t max_bytes) {
+  FILE *f = fopen(path.c_str(), "rb");
+  if (!f) return nh_set_error(NH_ERR_IO, "cannot open %s", path.c_str());
+  struct stat st;
+  if (fstat(fileno(f), &st)) {
+    fclose(f);
+    return nh_set_error(NH_ERR_IO, "cannot stat %s", path.c_str());
+  }
+  size_t n = (size_t)st.st_size;
+  if (n > max_bytes) n = max_bytes;
+  out.resize(n);
+  if (n && fread(out.data(), 1, n, f) != n) {
+    fclose(f);
+    return nh_set_error(NH_ERR_IO, "short read on %s", path.c_str());
+  }
+  fclose(f);
+  return NH_OK;
+}
+
+static bool file_exists(const std::string &p) {
+  struct stat st;
+  return stat(p.c_str(), &st) == 0 && S_ISREG(st.st_mode);
+}
+
+/* validate_db_directory (src/lib.rs:119-141): the three files in dir or dir/db */
+int nh_resolve_db_dir(const char *db_dir, std::string &out) {
+  const char *req[3] = {"hash.k2d", "opts.k2d", "taxo.k2d"};
+  std::string cands[2] = {std::string(db_dir), std::string(db_dir) + "/db"};
+  for (auto &c : cands) {
+    bool all = true;
+    for (auto r : req) all = all && file_exists(c + "/" + r);
+    if (all) {
+      out = c;
+      return NH_OK;
+    }
+  }
+  return nh_set_error(NH_ERR_IO, "Required files (hash.k2d, opts.k2d, taxo.k2d) not found in %s or %s/db",
+                      db_dir, db_dir);
+}
+
+static int parse_opts_taxo(nh_db *db, const void *opts, size_t opts_len, const void *taxo,
+                           size_t taxo_len) {
+  /* opts.k2d: raw IndexOptions, up to 64 bytes; older DBs are shorter */
+  uint8_t ob[64];
+  memset(ob, 0, sizeof ob);
+  if (opts_len < 32) return nh_set_error(NH_ERR_IO, "opts.k2d too short (%zu bytes)", opts_len);
+  memcpy(ob, opts, opts_len < 64 ? opts_len : 64);
+  nh_db_info_t &I = db->info;
+  memcpy(&I.k, ob + 0, 8);
+  memcpy(&I.l, ob + 8, 8);
+  memcpy(&I.spaced_seed_mask, ob + 16, 8);
+  memcpy(&I.toggle_mask, ob + 24, 8);
+  I.dna_db = ob[32] ? 1 : 0;
+  memcpy(&I.minimum_acceptable_hash_value, ob + 40, 8);
+  memcpy(&I.revcom_version, ob + 48, 4);
+  /* taxo.k2d */
+  const uint8_t *tb = (const uint8_t *)taxo;
+  if (taxo_len < 32 || memcmp(tb, "K2TAXDAT", 8))
+    return nh_set_error(NH_ERR_IO, "taxo.k2d: bad magic");
+  uint64_t node_count, name_len, rank_len;
+  memcpy(&node_count, tb + 8, 8);
+  memcpy(&name_len, tb + 16, 8);
+  memcpy(&rank_len, tb + 24, 8);
+  if (node_count == 0 || node_count > (1ULL << 31) ||
+      taxo_len < 32 + node_count * 56)
+    return nh_set_error(NH_ERR_IO, "taxo.k2d: truncated (%llu nodes)", (unsigned long long)node_count);
+  I.node_count = node_count;
+  db->h_parent.resize(node_count);
+  db->h_ext.resize(node_count);
+  db->h_ext64.resize(node_count);
+  for (uint64_t i = 0; i < node_count; i++) {
+    uint64_t parent, ext;
+    memcpy(&parent, tb + 32 + i * 56 + 0, 8);
+    memcpy(&ext, tb + 32 + i * 56 + 40, 8);
+    if (i > 0 && parent >= i)
+      return nh_set_error(NH_ERR_UNSUPPORTED,
+                          "taxo.k2d: node %llu has parent %llu (kraken2 taxonomies have parent < child)",
+                          (unsigned long long)i, (unsigned long long)parent);
+    if (ext > 0xFFFFFFFFULL)
+      return nh_set_error(NH_ERR_UNSUPPORTED, "taxo.k2d: external id %llu does not fit 32 bits",
+                          (unsigned long long)ext);
+    db->h_parent[i] = (uint32_t)parent;
+    db->h_ext[i] = (uint32_t)ext;
+    db->h_ext64[i] = ext;
+  }
+  db->h_parent[0] = 0;
+  return NH_OK;
+}
+
+static int finish_db(nh_db *db, const uint64_t hdr[4]) {
+  nh_db_info_t &I = db->info;
+  I.capacity = hdr[0];
+  I.size = hdr[1];
+  I.key_bits = hdr[2];
+  I.value_bits = hdr[3];
+  if (I.key_bits + I.value_bits != 32 || I.value_bits < 1 || I.value_bits > 31)
+    return nh_set_error(NH_ERR_IO, "hash.k2d: key_bits %llu + value_bits %llu != 32",
+                        (unsigned long long)I.key_bits, (unsigned long long)I.value_bits);
+  if (I.capacity == 0 || I.capacity >= (1ULL << 62))
+    return nh_set_error(NH_ERR_IO, "hash.k2d: bad capacity");
+  if (!I.dna_db) return nh_set_error(NH_ERR_UNSUPPORTED, "protein databases are not supported");
+  if (I.l < 1 || I.l > 31 || I.k < I.l)
+    return nh_set_error(NH_ERR_UNSUPPORTED, "unsupported k=%llu l=%llu", (unsigned long long)I.k,
+                        (unsigned long long)I.l);
+  if (I.k - I.l + 1 > NH_MAX_WINDOW)
+    return nh_set_error(NH_ERR_UNSUPPORTED, "minimizer window k-l+1=%llu exceeds %d",
+                        (unsigned long long)(I.k - I.l + 1), NH_MAX_WINDOW);
+  if (I.node_count > (1ULL << I.value_bits))
+    return nh_set_error(NH_ERR_IO, "taxonomy has more nodes than value_bits can address");
+  NhDbParams &P = db->params;
+  memset(&P, 0, sizeof P);
+  P.cells = db->d_cells;
+  P.capacity = I.capacity;
+  nh_divisor dv = nh_make_divisor(I.capacity);
+  P.mod_m = dv.m;
+  P.mod_sh1 = dv.sh1;
+  P.mod_sh2 = dv.sh2;
+  P.value_bits = (uint32_t)I.value_bits;
+  P.value_mask = (uint32_t)((1ULL << I.value_bits) - 1);
+  P.k = (int32_t)I.k;
+  P.l = (int32_t)I.l;
+  P.w = P.k - P.l + 1;
+  P.tile_pos = NH_TILE_LMERS - (P.w - 1);
+  P.amb_span = P.l > P.k - 1 ? P.l : P.k - 1;
+  P.revcom_version = I.revcom_version;
+  const uint64_t lmer_mask = (1ULL << (2 * I.l)) - 1;
+  P.seed_mask = I.spaced_seed_mask ? I.spaced_seed_mask : lmer_mask;
+  P.toggle = I.toggle_mask & lmer_mask;
+  P.min_hash = I.minimum_acceptable_hash_value;
+  P.node_count = (uint32_t)I.node_count;
+  CUDA_TRY(cudaMalloc(&db->d_parent, I.node_count * 4));
+  CUDA_TRY(cudaMalloc(&db->d_ext, I.node_count * 4));
+  CUDA_TRY(cudaMemcpy(db->d_parent, db->h_parent.data(), I.node_count * 4, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(db->d_ext, db->h_ext.data(), I.node_count * 4, cudaMemcpyHostToDevice));
+  P.parent = db->d_parent;
+  P.ext_id = db->d_ext;
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, db->info.device));
+  db->sm_count = prop.multiProcessorCount;
+  CUDA_TRY(nh_kernels_init());
+  return NH_OK;
+}
+
+static int select_device(int device) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    return nh_set_error(NH_ERR_CUDA, "no CUDA device available (%s); libnohuman_gpu has no CPU path",
+                        e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+  }
+  if (device < 0 || device >= n) return nh_set_error(NH_ERR_INVALID, "device %d out of range (%d devices)", device, n);
+  CUDA_TRY(cudaSetDevice(device));
+  return NH_OK;
+}
+
+extern "C" int nh_db_open_memory(const void *opts, size_t opts_len, const void *taxo, size_t taxo_len,
+                                 const uint64_t hash_header[4], const uint32_t *cells,
+                                 int cells_on_device, int device, nh_db **out) {
+  if (!opts || !taxo || !hash_header || !cells || !out) return nh_set_error(NH_ERR_INVALID, "null argument");
+  int rc = select_device(device);
+  if (rc) return rc;
+  nh_db *db = new nh_db();
+  db->info.device = device;
+  rc = parse_opts_taxo(db, opts, opts_len, taxo, taxo_len);
+  if (rc) {
+    delete db;
+    return rc;
+  }
+  const uint64_t cap = hash_header[0];
+  if (cells_on_device) {
+    if (((uintptr_t)cells & 31u) != 0) {
+      delete db;
+      return nh_set_error(NH_ERR_INVALID, "device cell array must be 32-byte aligned");
+    }
+    db->d_cells = const_cast<uint32_t *>(cells);
+    db->owns_cells = false;
+  } else {
+    /* padded to whole sectors so the last sector load stays inside the allocation */
+    const size_t bytes = ((cap + 7) / 8) * 32;
+    cudaError_t e = cudaMalloc(&db->d_cells, bytes);
+    if (e != cudaSuccess) {
+      delete db;
+      return nh_set_error(NH_ERR_NOMEM, "cudaMalloc(%zu) for the hash table failed: %s", bytes,
+                          cudaGetErrorString(e));
+    }
+    db->owns_cells = true;
+    cudaMemset(db->d_cells, 0, bytes);
+    e = cudaMemcpy(db->d_cells, cells, cap * 4, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+      nh_db_close(db);
+      return nh_set_error(NH_ERR_CUDA, "copying the hash table to the device failed: %s",
+                          cudaGetErrorString(e));
+    }
+  }
+  rc = finish_db(db, hash_header);
+  if (rc) {
+    nh_db_close(db);
+    return rc;
+  }
+  *out = db;
+  return NH_OK;
+}
+
+extern "C" int nh_db_open(const char *db_dir, int device, nh_db **out) {
+  if (!db_dir || !out) return nh_set_error(NH_ERR_INVALID, "null argument");
+  std::string dir;
+  int rc = nh_resolve_db_dir(db_dir, dir);
+  if (rc) return rc;
+  rc = select_device(device);
+  if (rc) return rc;
+  std::vector<uint8_t> opts, taxo;
+  if ((rc = read_file(dir + "/opts.k2d", opts, 64))) return rc;
+  if ((rc = read_file(dir + "/taxo.k2d", taxo, (size_t)-1))) return rc;
+  /* hash.k2d: 32-byte header, then capacity x u32; streamed through a pinned
+   * staging buffer so that the multi-GB table never needs a second host copy */
+  std::string hp = dir + "/hash.k2d";
+  FILE *f = fopen(hp.c_str(), "rb");
+  if (!f) return nh_set_error(NH_ERR_IO, "cannot open %s", hp.c_str());
+  uint64_t hdr[4];
+  if (fread(hdr, 8, 4, f) != 4) {
+    fclose(f);
+    return nh_set_error(NH_ERR_IO, "hash.k2d: short header");
+  }
+  struct stat st;
+  fstat(fileno(f), &st);
+  if ((uint64_t)st.st_size != 32 + hdr[0] * 4) {
+    fclose(f);
+    return nh_set_error(NH_ERR_IO, "hash.k2d: size %lld != 32 + 4*capacity(%llu)", (long long)st.st_size,
+                        (unsigned long long)hdr[0]);
+  }
+  nh_db *db = new nh_db();
+  db->info.device = device;
+  rc = parse_opts_taxo(db, opts.data(), opts.size(), taxo.data(), taxo.size());
+  if (rc) {
+    fclose(f);
+    delete db;
+    return rc;
+  }
+  const uint64_t cap = hdr[0];
+  const size_t bytes = ((cap + 7) / 8) * 32;
+  cudaError_t e = cudaMalloc(&db->d_cells, bytes);
+  if (e != cudaSuccess) {
+    fclose(f);
+    delete db;
+    return nh_set_error(NH_ERR_NOMEM, "cudaMalloc(%zu) for the hash table failed: %s", bytes,
+                        cudaGetErrorString(e));
+  }
+  db->owns_cells = true;
+  cudaMemset(db->d_cells, 0, bytes);
+  const size_t CH = 64u << 20;
+  uint8_t *stage[2] = {nullptr, nullptr};
+  cudaStream_t cs;
+  cudaStreamCreate(&cs);
+  cudaEvent_t ev[2];
+  for (int i = 0; i < 2; i++) {
+    cudaHostAlloc(&stage[i], CH, cudaHostAllocDefault);
+    cudaEventCreate(&ev[i]);
+  }
+  size_t total = cap * 4, done = 0;
+  int slot = 0;
+  rc = NH_OK;
+  while (done < total && stage[0] && stage[1]) {
+    size_t n = total - done < CH ? total - done : CH;
+    cudaEventSynchronize(ev[slot]);
+    if (fread(stage[slot], 1, n, f) != n) {
+      rc = nh_set_error(NH_ERR_IO, "hash.k2d: short read");
+      break;
+    }
+    cudaMemcpyAsync((uint8_t *)db->d_cells + done, stage[slot], n, cudaMemcpyHostToDevice, cs);
+    cudaEventRecord(ev[slot], cs);
+    done += n;
+    slot ^= 1;
+  }
+  if (!stage[0] || !stage[1]) rc = nh_set_error(NH_ERR_NOMEM, "pinned staging allocation failed");
+  cudaStreamSynchronize(cs);
+  for (int i = 0; i < 2; i++) {
+    if (stage[i]) cudaFreeHost(stage[i]);
+    cudaEventDestroy(ev[i]);
+  }
+  cudaStreamDestroy(cs);
+  fclose(f);
+  if (rc == NH_OK) {
+    e = cudaGetLastError();
+    if (e != cudaSuccess) rc = nh_set_error(NH_ERR_CUDA, "table upload failed: %s", cudaGetErrorString(e));
+  }
+  if (rc == NH_OK) rc = finish_db(db, hdr);
+  if (rc) {
+    nh_db_close(db);
+    return rc;
+  }
+  *out = db;
+  return NH_OK;
+}
+
+extern "C" int nh_db_info(const nh_db *db, nh_db_info_t *out) {
+  if (!db || !out) return nh_set_error(NH_ERR_INVALID, "null argument");
+  *out = db->info;
+  return NH_OK;
+}
+
+extern "C" const uint32_t *nh_db_device_cells(const nh_db *db) { return db ? db->d_cells : nullptr; }
+
+extern "C" void nh_db_close(nh_db *db) {
+  if (!db) return;
+  cudaSetDevice(db->info.device);
+  if (db->owns_cells && db->d_cells) cudaFree(db->d_cells);
+  if (db->d_parent) cudaFree(db->d_parent);
+  if (db->d_ext) cudaFree(db->d_ext);
+  delete db;
+}
+
+/* ------------------------------------------------------------------ */
+/* session                                                             */
+
+template <typename T>
+static cudaError_t dmalloc(T **p, size_t n) {
+  return cudaMalloc((void **)p, n * sizeof(T));
+}
+
+extern "C" int nh_session_create(nh_db *db, const nh_params_t *params, nh_session **out) {
+  if (!db || !params || !out) return nh_set_error(NH_ERR_INVALID, "null argument");
+  if (!(params->confidence >= 0.0 && params->confidence <= 1.0))
+    return nh_set_error(NH_ERR_INVALID, "Confidence score must be between 0 and 1");
+  CUDA_TRY(cudaSetDevice(db->info.device));
+  nh_session *s = new nh_session();
+  s->db = db;
+  s->params = *params;
+  if (s->params.minimum_hit_groups < 0) s->params.minimum_hit_groups = 2;
+  if (s->params.threads <= 0) s->params.threads = 1;
+  uint64_t mb = params->max_batch_bases ? params->max_batch_bases : (256ULL << 20);
+  if (mb > (1ULL << 31)) {
+    delete s;
+    return nh_set_error(NH_ERR_INVALID, "max_batch_bases must be <= 2^31");
+  }
+  uint64_t ms = params->max_batch_seqs ? params->max_batch_seqs : mb / 64 + 1024;
+  if (ms > (1ULL << 31)) ms = 1ULL << 31;
+  if (params->paired) ms += ms & 1;
+  s->cap_bases = mb;
+  s->cap_seqs = ms;
+  const NhDbParams &P = db->params;
+  /* every sequence has at most ceil(positions / tile_pos) tiles */
+  s->cap_tiles = ms + mb / (uint64_t)P.tile_pos + 1;
+  /* one lookup per k-mer position at most */
+  s->cap_lookups = mb;
+  cudaError_t e = cudaSuccess;
+#define ALLOC(ptr, n)                                     \
+  if (e == cudaSuccess) e = dmalloc(&(ptr), (size_t)(n)); \
+  if (e == cudaSuccess) s->device_bytes += (size_t)(n) * sizeof(*(ptr));
+  ALLOC(s->d_bases, mb + 64);
+  ALLOC(s->d_offsets, ms + 1);
+  ALLOC(s->d_tile_base, ms + 2);
+  ALLOC(s->d_block_sums, ms / 1024 + 2);
+  ALLOC(s->d_tiles, s->cap_tiles);
+  ALLOC(s->d_tile_out, s->cap_tiles);
+  ALLOC(s->d_lk_min, s->cap_lookups);
+  ALLOC(s->d_lk_cnt, s->cap_lookups);
+  ALLOC(s->d_lk_taxon, s->cap_lookups);
+  ALLOC(s->d_out_call, ms);
+  ALLOC(s->d_out_keep, ms);
+  ALLOC(s->d_dbg_call, ms);
+  ALLOC(s->d_dbg_total, ms);
+  ALLOC(s->d_dbg_groups, ms);
+  ALLOC(s->d_overflow, ms);
+  ALLOC(s->d_counters, 1);
+#undef ALLOC
+  if (e == cudaSuccess) e = cudaHostAlloc(&s->h_counters, sizeof(NhCounters), cudaHostAllocDefault);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
+  for (int i = 0; i < NH_NUM_EVENTS && e == cudaSuccess; i++) e = cudaEventCreate(&s->ev[i]);
+  if (e == cudaSuccess) e = cudaMemset(s->d_counters, 0, sizeof(NhCounters));
+  if (e != cudaSuccess) {
+    int rc = nh_set_error(e == cudaErrorMemoryAllocation ? NH_ERR_NOMEM : NH_ERR_CUDA,
+                          "session allocation failed: %s", cudaGetErrorString(e));
+    nh_session_destroy(s);
+    return rc;
+  }
+  memset(s->h_counters, 0, sizeof(NhCounters));
+  *out = s;
+  return NH_OK;
+}
+
+extern "C" void nh_session_destroy(nh_session *s) {
+  if (!s) return;
+  cudaSetDevice(s->db->info.device);
+  if (s->stream) cudaStreamSynchronize(s->stream);
+  cudaFree(s->d_bases);
+  cudaFree(s->d_offsets);
+  cudaFree(s->d_tile_base);
+  cudaFree(s->d_block_sums);
+  cudaFree(s->d_tiles);
+  cudaFree(s->d_tile_out);
+  cudaFree(s->d_lk_min);
+  cudaFree(s->d_lk_cnt);
+  cudaFree(s->d_lk_taxon);
+  cudaFree(s->d_out_call);
+  cudaFree(s->d_out_keep);
+  cudaFree(s->d_dbg_call);
+  cudaFree(s->d_dbg_total);
+  cudaFree(s->d_dbg_groups);
+  cudaFree(s->d_overflow);
+  cudaFree(s->d_counters);
+  if (s->h_counters) cudaFreeHost(s->h_counters);
+  for (int i = 0; i < NH_NUM_EVENTS; i++)
+    if (s->ev[i]) cudaEventDestroy(s->ev[i]);
+  if (s->stream) cudaStreamDestroy(s->stream);
+  delete s;
+}
+
+extern "C" void *nh_session_stream(nh_session *s) { return s ? (void *)s->stream : nullptr; }
+
+extern "C" void *nh_host_alloc(size_t bytes) {
+  void *p = nullptr;
+  if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) {
+    cudaGetLastError();
+    nh_set_error(NH_ERR_NOMEM, "cudaHostAlloc(%zu) failed", bytes);
+    return nullptr;
+  }
+  return p;
+}
+
+extern "C" void nh_host_free(void *p) {
+  if (p) cudaFreeHost(p);
+}
+
+/* Enqueue the four stages for a batch whose inputs are already on the device. */
+static int enqueue_batch(nh_session *s, const uint8_t *d_bases, const uint64_t *d_offsets,
+                         uint64_t n_seqs, uint64_t total_bases, uint32_t *d_out_call,
+                         uint8_t *d_out_keep, bool with_debug, const uint64_t *d_pos_off,
+                         uint64_t *d_pos_min, uint8_t *d_pos_amb) {
+  const NhDbParams &P = s->db->params;
+  NhBatchPtrs B;
+  memset(&B, 0, sizeof B);
+  B.bases = d_bases;
+  B.offsets = d_offsets;
+  B.n_seqs = (uint32_t)n_seqs;
+  B.paired = s->params.paired ? 1 : 0;
+  B.n_units = (uint32_t)(B.paired ? n_seqs / 2 : n_seqs);
+  B.tile_base = s->d_tile_base;
+  B.block_sums = s->d_block_sums;
+  B.tiles = s->d_tiles;
+  B.tile_out = s->d_tile_out;
+  B.lk_min = s->d_lk_min;
+  B.lk_cnt = s->d_lk_cnt;
+  B.lk_taxon = s->d_lk_taxon;
+  B.out_call = d_out_call;
+  B.out_keep = d_out_keep;
+  if (with_debug) {
+    B.dbg_call = s->d_dbg_call;
+    B.dbg_total_kmers = s->d_dbg_total;
+    B.dbg_hit_groups = s->d_dbg_groups;
+  }
+  B.overflow_units = s->d_overflow;
+  B.counters = s->d_counters;
+  B.dbg_pos_offsets = d_pos_off;
+  B.dbg_pos_min = d_pos_min;
+  B.dbg_pos_ambig = d_pos_amb;
+  NhScoreParams SP;
+  SP.confidence = s->params.confidence;
+  SP.min_hit_groups = s->params.minimum_hit_groups;
+  SP.keep_human = s->params.keep_human;
+  const int sm = s->db->sm_count;
+  uint64_t tiles_upper = n_seqs + total_bases / (uint64_t)P.tile_pos + 1;
+  uint64_t lookups_upper = total_bases;
+  int launches = 0;
+  cudaStream_t st = s->stream;
+  cudaEventRecord(s->ev[EV_PLAN0], st);
+  launches += nh_launch_plan(P, B, st);
+  cudaEventRecord(s->ev[EV_MIN0], st);
+  launches += nh_launch_minimizers(P, B, (uint32_t)tiles_upper, sm, st);
+  cudaEventRecord(s->ev[EV_PROBE0], st);
+  launches += nh_launch_probe(P, s->d_lk_min, s->d_lk_taxon, &s->d_counters->n_lookups,
+                              (uint32_t)lookups_upper, sm, st);
+  cudaEventRecord(s->ev[EV_SCORE0], st);
+  launches += nh_launch_score(P, B, SP, sm, st);
+  cudaEventRecord(s->ev[EV_SCORE1], st);
+  cudaMemcpyAsync(s->h_counters, s->d_counters, sizeof(NhCounters), cudaMemcpyDeviceToHost, st);
+  s->last_launches = (uint32_t)launches;
+  s->last_units = B.n_units;
+  s->last_bases = total_bases;
+  s->pending = true;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return nh_set_error(NH_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+  return NH_OK;
+}
+
+static int check_batch_args(nh_session *s, uint64_t n_seqs, uint64_t total_bases) {
+  if (s->params.paired && (n_seqs & 1))
+    return nh_set_error(NH_ERR_INVALID, "paired session needs an even number of sequences");
+  if (n_seqs > s->cap_seqs)
+    return nh_set_error(NH_ERR_CAPACITY, "batch has %llu sequences, session capacity is %llu",
+                        (unsigned long long)n_seqs, (unsigned long long)s->cap_seqs);
+  if (total_bases > s->cap_bases)
+    return nh_set_error(NH_ERR_CAPACITY, "batch has %llu bases, session capacity is %llu",
+                        (unsigned long long)total_bases, (unsigned long long)s->cap_bases);
+  return NH_OK;
+}
+
+extern "C" int nh_session_sync(nh_session *s, nh_batch_stats_t *stats) {
+  if (!s) return nh_set_error(NH_ERR_INVALID, "null session");
+  CUDA_TRY(cudaSetDevice(s->db->info.device));
+  CUDA_TRY(cudaStreamSynchronize(s->stream));
+  if (s->pending && s->h_counters->error)
+    return nh_set_error(NH_ERR_UNSUPPORTED, "a read hit more than %d distinct taxa", NH_BIG_HASH_SLOTS);
+  if (stats) {
+    memset(stats, 0, sizeof *stats);
+    if (s->pending) {
+      const NhCounters &c = *s->h_counters;
+      stats->n_units = s->last_units;
+      stats->n_classified = c.n_classified;
+      stats->n_unclassified = s->last_units - c.n_classified;
+      stats->n_kept = c.n_kept;
+      stats->n_bases = s->last_bases;
+      stats->n_tiles = c.n_tiles;
+      stats->n_lookups = c.n_lookups;
+      cudaEventElapsedTime(&stats->ms_plan, s->ev[EV_PLAN0], s->ev[EV_MIN0]);
+      cudaEventElapsedTime(&stats->ms_minimizer, s->ev[EV_MIN0], s->ev[EV_PROBE0]);
+      cudaEventElapsedTime(&stats->ms_probe, s->ev[EV_PROBE0], s->ev[EV_SCORE0]);
+      cudaEventElapsedTime(&stats->ms_score, s->ev[EV_SCORE0], s->ev[EV_SCORE1]);
+      if (s->timed_copies) {
+        cudaEventElapsedTime(&stats->ms_h2d, s->ev[EV_H2D0], s->ev[EV_PLAN0]);
+        cudaEventElapsedTime(&stats->ms_d2h, s->ev[EV_SCORE1], s->ev[EV_D2H1]);
+      }
+      stats->gpu_launches = s->last_launches;
+    }
+  }
+  return NH_OK;
+}
+
+extern "C" int nh_classify_batch_device(nh_session *s, const uint8_t *d_bases,
+                                        const uint64_t *d_offsets, uint64_t n_seqs,
+                                        uint64_t total_bases, uint32_t *d_out_call,
+                                        uint8_t *d_out_keep) {
+  if (!s || !d_bases || !d_offsets) return nh_set_error(NH_ERR_INVALID, "null argument");
+  int rc = check_batch_args(s, n_seqs, total_bases);
+  if (rc) return rc;
+  CUDA_TRY(cudaSetDevice(s->db->info.device));
+  s->timed_copies = false;
+  if (n_seqs == 0) {
+    s->pending = false;
+    return NH_OK;
+  }
+  return enqueue_batch(s, d_bases, d_offsets, n_seqs, total_bases, d_out_call, d_out_keep, false,
+                       nullptr, nullptr, nullptr);
+}
+
+extern "C" int nh_classify_batch(nh_session *s, const uint8_t *bases, const uint64_t *offsets,
+                                 uint64_t n_seqs, uint32_t *out_call, uint8_t *out_keep,
+                                 nh_batch_stats_t *stats) {
+  if (!s || !offsets || (!bases && n_seqs && offsets[n_seqs] > 0))
+    return nh_set_error(NH_ERR_INVALID, "null argument");
+  const uint64_t total = n_seqs ? offsets[n_seqs] - offsets[0] : 0;
+  if (n_seqs && offsets[0] != 0) return nh_set_error(NH_ERR_INVALID, "offsets[0] must be 0");
+  int rc = check_batch_args(s, n_seqs, total);
+  if (rc) return rc;
+  CUDA_TRY(cudaSetDevice(s->db->info.device));
+  if (n_seqs == 0) {
+    s->pending = false;
+    if (stats) memset(stats, 0, sizeof *stats);
+    return NH_OK;
+  }
+  cudaStream_t st = s->stream;
+  const uint64_t n_units = s->params.paired ? n_seqs / 2 : n_seqs;
+  cudaEventRecord(s->ev[EV_H2D0], st);
+  if (total) CUDA_TRY(cudaMemcpyAsync(s->d_bases, bases, total, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(s->d_offsets, offsets, (n_seqs + 1) * 8, cudaMemcpyHostToDevice, st));
+  rc = enqueue_batch(s, s->d_bases, s->d_offsets, n_seqs, total, s->d_out_call, s->d_out_keep, true,
+                     nullptr, nullptr, nullptr);
+  if (rc) return rc;
+  if (out_call) CUDA_TRY(cudaMemcpyAsync(out_call, s->d_out_call, n_units * 4, cudaMemcpyDeviceToHost, st));
+  if (out_keep) CUDA_TRY(cudaMemcpyAsync(out_keep, s->d_out_keep, n_units, cudaMemcpyDeviceToHost, st));
+  cudaEventRecord(s->ev[EV_D2H1], st);
+  s->timed_copies = true;
+  return nh_session_sync(s, stats);
+}
+
+/* ------------------------------------------------------------------ */
+/* per-stage entry points for the parity tests                          */
+
+extern "C" int nh_debug_minimizers(nh_session *s, const uint8_t *bases, const uint64_t *offsets,
+                                   uint64_t n_seqs, const uint64_t *pos_offsets, uint64_t *out_min,
+                                   uint8_t *out_ambig) {
+  if (!s || !offsets || !pos_offsets || !out_min || !out_ambig)
+    return nh_set_error(NH_ERR_INVALID, "null argument");
+  if (n_seqs == 0) return NH_OK;
+  const uint64_t total = offsets[n_seqs];
+  int rc = check_batch_args(s, n_seqs & ~(uint64_t)(s->params.paired ? 1 : 0), total);
+  if (rc) return rc;
+  if (s->params.paired && (n_seqs & 1)) return nh_set_error(NH_ERR_INVALID, "odd sequence count");
+  CUDA_TRY(cudaSetDevice(s->db->info.device));
+  const uint64_t npos = pos_offsets[n_seqs];
+  uint64_t *d_pos_off = nullptr, *d_min = nullptr;
+  uint8_t *d_amb = nullptr;
+  CUDA_TRY(cudaMalloc(&d_pos_off, (n_seqs + 1) * 8));
+  CUDA_TRY(cudaMalloc(&d_min, (npos + 1) * 8));
+  CUDA_TRY(cudaMalloc(&d_amb, npos + 1));
+  cudaStream_t st = s->stream;
+  if (total) CUDA_TRY(cudaMemcpyAsync(s->d_bases, bases, total, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(s->d_offsets, offsets, (n_seqs + 1) * 8, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(d_pos_off, pos_offsets, (n_seqs + 1) * 8, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemsetAsync(d_min, 0xEE, (npos + 1) * 8, st));
+  CUDA_TRY(cudaMemsetAsync(d_amb, 0xEE, npos + 1, st));
+  rc = enqueue_batch(s, s->d_bases, s->d_offsets, n_seqs, total, s->d_out_call, s->d_out_keep, true,
+                     d_pos_off, d_min, d_amb);
+  if (rc == NH_OK) {
+    cudaMemcpyAsync(out_min, d_min, npos * 8, cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(out_ambig, d_amb, npos, cudaMemcpyDeviceToHost, st);
+    s->timed_copies = false;
+    rc = nh_session_sync(s, nullptr);
+  }
+  cudaFree(d_pos_off);
+  cudaFree(d_min);
+  cudaFree(d_amb);
+  return rc;
+}
+
+extern "C" int nh_debug_probe(nh_session *s, const uint64_t *keys, uint64_t n, uint32_t *out_taxon) {
+  if (!s || !keys || !out_taxon) return nh_set_error(NH_ERR_INVALID, "null argument");
+  if (n == 0) return NH_OK;
+  if (n > 0xFFFFFFFFULL) return nh_set_error(NH_ERR_CAPACITY, "too many keys");
+  CUDA_TRY(cudaSetDevice(s->db->info.device));
+  uint64_t *d_keys = nullptr;
+  uint32_t *d_tax = nullptr;
+  CUDA_TRY(cudaMalloc(&d_keys, n * 8));
+  CUDA_TRY(cudaMalloc(&d_tax, n * 4));
+  cudaStream_t st = s->stream;
+  CUDA_TRY(cudaMemcpyAsync(d_keys, keys, n * 8, cudaMemcpyHostToDevice, st));
+  nh_launch_probe(s->db->params, d_keys, d_tax, nullptr, (uint32_t)n, s->db->sm_count, st);
+  CUDA_TRY(cudaMemcpyAsync(out_taxon, d_tax, n * 4, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  cudaFree(d_keys);
+  cudaFree(d_tax);
+  return NH_OK;
+}
+
+extern "C" int nh_debug_last_batch(nh_session *s, uint32_t *out_call_internal,
+                                   uint32_t *out_total_kmers, uint32_t *out_hit_groups,
+                                   uint64_t n_units) {
+  if (!s) return nh_set_error(NH_ERR_INVALID, "null session");
+  if (n_units > s->last_units) return nh_set_error(NH_ERR_INVALID, "last batch had fewer units");
+  CUDA_TRY(cudaSetDevice(s->db->info.device));
+  CUDA_TRY(cudaStreamSynchronize(s->stream));
+  if (out_call_internal)
+    CUDA_TRY(cudaMemcpy(out_call_internal, s->d_dbg_call, n_units * 4, cudaMemcpyDeviceToHost));
+  if (out_total_kmers)
+    CUDA_TRY(cudaMemcpy(out_total_kmers, s->d_dbg_total, n_units * 4, cudaMemcpyDeviceToHost));
+  if (out_hit_groups)
+    CUDA_TRY(cudaMemcpy(out_hit_groups, s->d_dbg_groups, n_units * 4, cudaMemcpyDeviceToHost));
+  return NH_OK;
+}
+
+/* ------------------------------------------------------------------ */
+extern "C" int nh_bench_random_gather(nh_db *db, uint64_t n_reads, int iters, double *out_gbs) {
+  if (!db || !out_gbs || iters < 1) return nh_set_error(NH_ERR_INVALID, "bad argument");
+  CUDA_TRY(cudaSetDevice(db->info.device));
+  const uint64_t n_sectors = db->info.capacity / 8;
+  if (n_sectors == 0) return nh_set_error(NH_ERR_INVALID, "table too small");
+  uint32_t *sink = nullptr;
+  CUDA_TRY(cudaMalloc(&sink, 64));
+  cudaStream_t st;
+  CUDA_TRY(cudaStreamCreate(&st));
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  float best = 1e30f;
+  for (int i = 0; i < iters + 1; i++) { /* first launch is warm-up */
+    cudaEventRecord(e0, st);
+    nh_launch_random_gather(db->d_cells, n_sectors, n_reads, 0x1234567ULL * (uint64_t)(i + 1), sink,
+                            db->sm_count, st);
+    cudaEventRecord(e1, st);
+    cudaEventSynchronize(e1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (i > 0 && ms < best) best = ms;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaStreamDestroy(st);
+  cudaFree(sink);
+  CUDA_TRY(cudaGetLastError());
+  *out_gbs = (double)n_reads * 32.0 / ((double)best * 1e-3) / 1e9;
+  return NH_OK;
+}

@@ -1,0 +1,68 @@
+/* nh_internal.h — host-side objects behind the opaque C-ABI handles. */
+#ifndef NH_INTERNAL_H
+#define NH_INTERNAL_H
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/nohuman_gpu.h"
+#include "nh_kernels.cuh"
+
+enum {
+  EV_H2D0 = 0,
+  EV_PLAN0,
+  EV_MIN0,
+  EV_PROBE0,
+  EV_SCORE0,
+  EV_SCORE1,
+  EV_D2H1,
+  NH_NUM_EVENTS
+};
+
+struct nh_db {
+  nh_db_info_t info{};
+  NhDbParams params{};
+  uint32_t *d_cells = nullptr;
+  bool owns_cells = false;
+  uint32_t *d_parent = nullptr;
+  uint32_t *d_ext = nullptr;
+  std::vector<uint32_t> h_parent, h_ext;
+  std::vector<uint64_t> h_ext64;
+  int sm_count = 0;
+};
+
+struct nh_session {
+  nh_db *db = nullptr;
+  nh_params_t params{};
+  uint64_t cap_bases = 0, cap_seqs = 0, cap_tiles = 0, cap_lookups = 0;
+  size_t device_bytes = 0;
+  uint8_t *d_bases = nullptr;
+  uint64_t *d_offsets = nullptr;
+  uint32_t *d_tile_base = nullptr;
+  uint32_t *d_block_sums = nullptr;
+  NhTile *d_tiles = nullptr;
+  NhTileOut *d_tile_out = nullptr;
+  uint64_t *d_lk_min = nullptr;
+  uint8_t *d_lk_cnt = nullptr;
+  uint32_t *d_lk_taxon = nullptr;
+  uint32_t *d_out_call = nullptr;
+  uint8_t *d_out_keep = nullptr;
+  uint32_t *d_dbg_call = nullptr, *d_dbg_total = nullptr, *d_dbg_groups = nullptr;
+  uint32_t *d_overflow = nullptr;
+  NhCounters *d_counters = nullptr;
+  NhCounters *h_counters = nullptr; /* pinned */
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[NH_NUM_EVENTS] = {};
+  bool pending = false;
+  bool timed_copies = false;
+  uint32_t last_launches = 0;
+  uint64_t last_units = 0, last_bases = 0;
+};
+
+int nh_set_error(int code, const char *fmt, ...);
+int nh_resolve_db_dir(const char *db_dir, std::string &out);
+
+#endif

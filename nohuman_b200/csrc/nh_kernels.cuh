@@ -1,0 +1,110 @@
+/*
+ * nh_kernels.cuh — device-side parameter blocks and launch prototypes of the
+ * four classification stages (sm_100a).  See DESIGN.md for the data layout.
+ */
+#ifndef NH_KERNELS_CUH
+#define NH_KERNELS_CUH
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "nh_math.h"
+
+#define NH_WARPS_PER_BLOCK 8
+#define NH_BLOCK_THREADS (NH_WARPS_PER_BLOCK * 32)
+#define NH_TILE_LMERS 128           /* l-mers per minimizer tile (4 warp iterations) */
+#define NH_MAX_WINDOW 32            /* k - l + 1 must fit one warp */
+#define NH_SMEM_PARENT_MAX 8192     /* taxonomy nodes staged in shared memory */
+#define NH_WARP_HASH_SLOTS 64       /* per-read taxon->count table (fast path) */
+#define NH_BIG_HASH_SLOTS 16384     /* overflow path: one warp per block */
+#define NH_NONE64 0xFFFFFFFFFFFFFFFFULL
+
+/* Database constants every kernel needs (passed by value). */
+struct NhDbParams {
+  const uint32_t *cells;     /* capacity x u32, resident in HBM */
+  uint64_t capacity;
+  uint64_t mod_m;            /* nh_fastmod constants for capacity */
+  uint32_t mod_sh1, mod_sh2;
+  uint32_t value_bits;
+  uint32_t value_mask;
+  int32_t k, l, w;           /* w = k - l + 1 */
+  int32_t tile_pos;          /* k-mer positions per tile = NH_TILE_LMERS - (w-1) */
+  int32_t amb_span;          /* max(l, k-1): bases whose ambiguity voids a position */
+  int32_t revcom_version;
+  uint64_t seed_mask;        /* spaced_seed_mask, or the l-mer mask when it is 0 */
+  uint64_t toggle;           /* toggle_mask & lmer_mask */
+  uint64_t min_hash;         /* minimum_acceptable_hash_value */
+  const uint32_t *parent;    /* node_count x u32 */
+  const uint32_t *ext_id;    /* node_count x u32 */
+  uint32_t node_count;
+};
+
+struct NhTile {
+  uint32_t seq;       /* sequence index in the batch */
+  uint32_t pos_begin; /* first k-mer position of the tile */
+};
+
+struct NhTileOut {
+  uint32_t lk_off; /* first lookup of the tile in the lookup arrays */
+  uint32_t lk_cnt; /* number of lookups (distinct-consecutive minimizers) */
+};
+
+/* Device-side counters of one batch. */
+struct NhCounters {
+  uint32_t n_tiles;
+  uint32_t n_lookups;    /* allocation cursor of the lookup arrays */
+  uint32_t n_classified;
+  uint32_t n_kept;
+  uint32_t n_overflow;   /* units sent to the big-table scoring pass */
+  uint32_t error;        /* nonzero: a unit exceeded even the big table */
+  uint32_t pad[2];
+};
+
+struct NhBatchPtrs {
+  const uint8_t *bases;
+  const uint64_t *offsets;  /* n_seqs + 1 */
+  uint32_t n_seqs;
+  uint32_t n_units;
+  int32_t paired;
+  /* plan */
+  uint32_t *tile_base;      /* n_seqs + 1: first tile of each sequence */
+  uint32_t *block_sums;
+  NhTile *tiles;
+  NhTileOut *tile_out;
+  /* lookups */
+  uint64_t *lk_min;
+  uint8_t *lk_cnt;          /* k-mer positions that take this lookup's taxon */
+  uint32_t *lk_taxon;
+  /* results */
+  uint32_t *out_call;       /* external taxid per unit (may be null) */
+  uint8_t *out_keep;        /* may be null */
+  uint32_t *dbg_call;       /* internal id per unit (may be null) */
+  uint32_t *dbg_total_kmers;
+  uint32_t *dbg_hit_groups;
+  uint32_t *overflow_units;
+  NhCounters *counters;
+  /* per-position debug output of the minimizer kernel (may be null) */
+  const uint64_t *dbg_pos_offsets;
+  uint64_t *dbg_pos_min;
+  uint8_t *dbg_pos_ambig;
+};
+
+struct NhScoreParams {
+  double confidence;
+  int32_t min_hit_groups;
+  int32_t keep_human;
+};
+
+/* launchers (nh_kernels.cu); each returns the number of kernels launched */
+int nh_launch_plan(const NhDbParams &db, const NhBatchPtrs &b, cudaStream_t st);
+int nh_launch_minimizers(const NhDbParams &db, const NhBatchPtrs &b, uint32_t tiles_upper,
+                         int sm_count, cudaStream_t st);
+int nh_launch_probe(const NhDbParams &db, const uint64_t *keys, uint32_t *taxa,
+                    const uint32_t *n_dev, uint32_t n_upper, int sm_count, cudaStream_t st);
+int nh_launch_score(const NhDbParams &db, const NhBatchPtrs &b, const NhScoreParams &sp,
+                    int sm_count, cudaStream_t st);
+int nh_launch_random_gather(const uint32_t *cells, uint64_t n_sectors, uint64_t n_reads,
+                            uint64_t seed, uint32_t *sink, int sm_count, cudaStream_t st);
+cudaError_t nh_kernels_init(void);
+
+#endif

@@ -1,0 +1,727 @@
+/*
+ * k2_oracle.c — CPU restatement of kraken2's classification path.
+ * TEST INFRASTRUCTURE ONLY (see k2_oracle.h).  PARITY UNPINNED: the real
+ * kraken2 (pinned at /root/reference Dockerfile:15,35-38) is unavailable
+ * offline; every function cites the upstream unit it restates and the
+ * SURVEY.md appendix section that records the recalled behaviour.
+ *
+ * Boundary in the reference that this stands behind:
+ *   src/lib.rs:22-23   Command::new("kraken2").args(args).output()
+ *   src/main.rs:215-267 argv (--threads --db --output --confidence [--paired]
+ *                       --classified-out|--unclassified-out)
+ */
+#include "k2_oracle.h"
+
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+/* ------------------------------------------------------------------ */
+/* kv_store.h: MurmurHash3 finaliser                      */
+uint64_t k2o_fmix64(uint64_t k) {
+  k ^= k >> 33;
+  k *= 0xff51afd7ed558ccdULL;
+  k ^= k >> 33;
+  k *= 0xc4ceb9fe1a85ec53ULL;
+  k ^= k >> 33;
+  return k;
+}
+
+/* mmscanner.cc: MinimizerScanner::reverse_complement */
+uint64_t k2o_reverse_complement(uint64_t kmer, int n, int revcom_version) {
+  /* reverse 2-bit groups across the 64-bit word */
+  kmer = ((kmer & 0xCCCCCCCCCCCCCCCCULL) >> 2) | ((kmer & 0x3333333333333333ULL) << 2);
+  kmer = ((kmer & 0xF0F0F0F0F0F0F0F0ULL) >> 4) | ((kmer & 0x0F0F0F0F0F0F0F0FULL) << 4);
+  kmer = ((kmer & 0xFF00FF00FF00FF00ULL) >> 8) | ((kmer & 0x00FF00FF00FF00FFULL) << 8);
+  kmer = ((kmer & 0xFFFF0000FFFF0000ULL) >> 16) | ((kmer & 0x0000FFFF0000FFFFULL) << 16);
+  kmer = (kmer >> 32) | (kmer << 32);
+  if (revcom_version == 0) /* pre-2.0.8 databases: no shift (kept for old DBs) */
+    return (~kmer) & ((1ULL << (n * 2)) - 1);
+  return ((~kmer) >> (64 - n * 2)) & ((1ULL << (n * 2)) - 1);
+}
+
+uint64_t k2o_canonical(uint64_t kmer, int n, int revcom_version) {
+  uint64_t rc = k2o_reverse_complement(kmer, n, revcom_version);
+  return kmer < rc ? kmer : rc;
+}
+
+uint64_t k2o_spaced_seed_mask(int l, int spaces) {
+  /* template string '1' x (l-2s) then '01' x s read as base-2, each bit
+   * expanded to two bits (build-side helper) */
+  uint64_t tmpl = 0;
+  int i;
+  for (i = 0; i < l - 2 * spaces; i++) tmpl = (tmpl << 1) | 1;
+  for (i = 0; i < spaces; i++) tmpl = (tmpl << 2) | 1;
+  uint64_t mask = 0;
+  for (i = l - 1; i >= 0; i--) {
+    mask <<= 2;
+    if ((tmpl >> i) & 1) mask |= 3;
+  }
+  return mask;
+}
+
+/* ------------------------------------------------------------------ */
+/* MinimizerScanner (mmscanner.{h,cc})                 */
+
+static uint8_t g_lookup[256];
+static int g_lookup_ready = 0;
+static void init_lookup(void) {
+  if (g_lookup_ready) return;
+  memset(g_lookup, 0xFF, sizeof g_lookup);
+  g_lookup['A'] = g_lookup['a'] = 0;
+  g_lookup['C'] = g_lookup['c'] = 1;
+  g_lookup['G'] = g_lookup['g'] = 2;
+  g_lookup['T'] = g_lookup['t'] = 3;
+  g_lookup_ready = 1;
+}
+
+int k2o_scanner_init(k2o_scanner *s, int64_t k, int64_t l, uint64_t spaced_seed_mask, int dna,
+                     uint64_t toggle_mask, int revcom_version) {
+  init_lookup();
+  memset(s, 0, sizeof *s);
+  if (l > 31 || l < 1 || k < l) return -1;
+  s->k = k;
+  s->l = l;
+  s->spaced_seed_mask = spaced_seed_mask;
+  s->dna = dna;
+  s->revcom_version = revcom_version;
+  s->lmer_mask = (1ULL << (l * 2)) - 1;
+  s->toggle_mask = toggle_mask & s->lmer_mask;
+  s->qcap = k - l + 4;
+  s->queue = (k2o_mmdata *)malloc(sizeof(k2o_mmdata) * (size_t)s->qcap);
+  s->last_minimizer = ~0ULL;
+  return s->queue ? 0 : -1;
+}
+
+void k2o_scanner_free(k2o_scanner *s) {
+  free(s->queue);
+  s->queue = NULL;
+}
+
+void k2o_scanner_load(k2o_scanner *s, const char *seq, size_t len) {
+  s->str = seq;
+  s->str_len = len;
+  s->start = 0;
+  s->finish = len;
+  s->str_pos = s->start;
+  if ((int64_t)(s->finish - s->start) + 1 < s->l) /* interval shorter than an l-mer */
+    s->str_pos = s->finish;
+  s->qhead = 0;
+  s->qlen = 0;
+  s->queue_pos = 0;
+  s->loaded_ch = 0;
+  s->last_minimizer = ~0ULL;
+  s->last_ambig = 0;
+}
+
+#define QAT(s, i) ((s)->queue[((s)->qhead + (i)) % (s)->qcap])
+
+uint64_t *k2o_scanner_next(k2o_scanner *s) {
+  if (s->str_pos >= s->finish) return NULL;
+  int changed_minimizer = 0;
+  while (!changed_minimizer) {
+    if (s->loaded_ch == s->l) s->loaded_ch--;
+    while (s->loaded_ch < s->l && s->str_pos < s->finish) {
+      s->loaded_ch++;
+      s->lmer <<= 2;
+      s->last_ambig <<= 2;
+      uint8_t code = g_lookup[(uint8_t)s->str[s->str_pos++]];
+      if (code == 0xFF) {
+        s->qlen = 0;
+        s->qhead = 0;
+        s->queue_pos = 0;
+        s->lmer = 0;
+        s->loaded_ch = 0;
+        s->last_ambig |= 3;
+      } else {
+        s->lmer |= code;
+      }
+      s->lmer &= s->lmer_mask;
+      s->last_ambig &= s->lmer_mask;
+      /* first k-mer not yet filled: keep loading; l-mer incomplete after
+       * that: return (caller sees is_ambiguous()) */
+      if ((int64_t)(s->str_pos - s->start) >= s->k && s->loaded_ch < s->l)
+        return &s->last_minimizer;
+    }
+    if (s->loaded_ch < s->l) return NULL;
+    uint64_t canonical =
+        s->dna ? k2o_canonical(s->lmer, (int)s->l, s->revcom_version) : s->lmer;
+    if (s->spaced_seed_mask) canonical &= s->spaced_seed_mask;
+    uint64_t candidate = canonical ^ s->toggle_mask;
+    if (s->k == s->l) {
+      s->last_minimizer = candidate ^ s->toggle_mask;
+      return &s->last_minimizer;
+    }
+    while (s->qlen > 0 && QAT(s, s->qlen - 1).candidate > candidate) s->qlen--;
+    if (s->qlen == 0 && s->queue_pos >= s->k - s->l) changed_minimizer = 1;
+    QAT(s, s->qlen).candidate = candidate;
+    QAT(s, s->qlen).pos = s->queue_pos;
+    s->qlen++;
+    if (QAT(s, 0).pos < s->queue_pos - s->k + s->l) {
+      s->qhead = (s->qhead + 1) % s->qcap;
+      s->qlen--;
+      changed_minimizer = 1;
+    }
+    if (s->queue_pos == s->k - s->l) changed_minimizer = 1;
+    s->queue_pos++;
+    /* return once per k-mer once a full k-mer's worth of chars was read */
+    if (s->str_pos >= (size_t)s->k) break;
+  }
+  s->last_minimizer = QAT(s, 0).candidate ^ s->toggle_mask;
+  return &s->last_minimizer;
+}
+
+int k2o_scanner_is_ambiguous(const k2o_scanner *s) {
+  return (s->queue_pos < s->k - s->l) || (s->last_ambig != 0);
+}
+
+size_t k2o_scan_positions(const k2o_index_options *o, const char *seq, size_t len,
+                          uint64_t *out_min, uint8_t *out_ambig, size_t cap) {
+  k2o_scanner sc;
+  if (k2o_scanner_init(&sc, (int64_t)o->k, (int64_t)o->l, o->spaced_seed_mask, o->dna_db,
+                       o->toggle_mask, o->revcom_version))
+    return 0;
+  k2o_scanner_load(&sc, seq, len);
+  size_t n = 0;
+  uint64_t *m;
+  while ((m = k2o_scanner_next(&sc)) != NULL) {
+    if (n < cap) {
+      if (out_min) out_min[n] = *m;
+      if (out_ambig) out_ambig[n] = (uint8_t)k2o_scanner_is_ambiguous(&sc);
+    }
+    n++;
+  }
+  k2o_scanner_free(&sc);
+  return n;
+}
+
+/* ------------------------------------------------------------------ */
+/* CompactHashTable (compact_hash.cc, built with -DLINEAR_PROBING)     */
+
+int k2o_cht_alloc(k2o_cht *t, uint64_t capacity, uint64_t value_bits) {
+  if (value_bits < 1 || value_bits > 31 || capacity == 0) return -1;
+  t->capacity = capacity;
+  t->size = 0;
+  t->value_bits = value_bits;
+  t->key_bits = 32 - value_bits;
+  t->cells = (uint32_t *)calloc(capacity, sizeof(uint32_t));
+  t->owns_cells = 1;
+  return t->cells ? 0 : -1;
+}
+
+void k2o_cht_free(k2o_cht *t) {
+  if (t->owns_cells) free(t->cells);
+  t->cells = NULL;
+}
+
+uint32_t k2o_cht_get_stats(const k2o_cht *t, uint64_t key, uint64_t *cells, uint64_t *sectors) {
+  uint64_t hc = k2o_fmix64(key);
+  uint64_t compacted_key = hc >> (32 + t->value_bits);
+  uint64_t idx = hc % t->capacity;
+  uint64_t first_idx = idx;
+  uint32_t vmask = (uint32_t)((1ULL << t->value_bits) - 1);
+  uint64_t ncell = 0, nsect = 0, last_sector = ~0ULL;
+  uint32_t result = 0;
+  for (;;) {
+    uint32_t cell = t->cells[idx];
+    ncell++;
+    if ((idx >> 3) != last_sector) {
+      last_sector = idx >> 3;
+      nsect++;
+    }
+    uint32_t val = cell & vmask;
+    if (!val) break; /* empty cell ends the probe */
+    if ((uint64_t)(cell >> t->value_bits) == compacted_key) {
+      result = val;
+      break;
+    }
+    idx += 1; /* second_hash() == 1 under LINEAR_PROBING */
+    idx %= t->capacity;
+    if (idx == first_idx) break;
+  }
+  if (cells) *cells += ncell;
+  if (sectors) *sectors += nsect;
+  return result;
+}
+
+uint32_t k2o_cht_get(const k2o_cht *t, uint64_t key) {
+  return k2o_cht_get_stats(t, key, NULL, NULL);
+}
+
+int k2o_cht_insert_lca(k2o_cht *t, const k2o_taxonomy *tax, uint64_t key, uint32_t taxon) {
+  /* CompareAndSet loop of build_db.cc collapsed: value := LCA(existing, taxon) */
+  uint64_t hc = k2o_fmix64(key);
+  uint64_t compacted_key = hc >> (32 + t->value_bits);
+  uint64_t idx = hc % t->capacity;
+  uint64_t first_idx = idx;
+  uint32_t vmask = (uint32_t)((1ULL << t->value_bits) - 1);
+  for (;;) {
+    uint32_t cell = t->cells[idx];
+    uint32_t val = cell & vmask;
+    if (!val) {
+      t->cells[idx] = (uint32_t)(compacted_key << t->value_bits) | taxon;
+      t->size++;
+      return 0;
+    }
+    if ((uint64_t)(cell >> t->value_bits) == compacted_key) {
+      uint32_t nv = (uint32_t)k2o_lca(tax, val, taxon);
+      t->cells[idx] = (uint32_t)(compacted_key << t->value_bits) | nv;
+      return 0;
+    }
+    idx = (idx + 1) % t->capacity;
+    if (idx == first_idx) return -1; /* table full */
+  }
+}
+
+/* ------------------------------------------------------------------ */
+/* Taxonomy (taxonomy.cc)                                  */
+
+int k2o_is_a_ancestor_of_b(const k2o_taxonomy *t, uint64_t a, uint64_t b) {
+  if (!a || !b) return 0;
+  while (b > a) b = t->nodes[b].parent_id;
+  return b == a;
+}
+
+uint64_t k2o_lca(const k2o_taxonomy *t, uint64_t a, uint64_t b) {
+  if (!a || !b) return a ? a : b;
+  while (a != b) {
+    if (a > b)
+      a = t->nodes[a].parent_id;
+    else
+      b = t->nodes[b].parent_id;
+  }
+  return a;
+}
+
+uint64_t k2o_taxonomy_internal_id(const k2o_taxonomy *t, uint64_t ext_id) {
+  uint64_t i;
+  for (i = 1; i < t->node_count; i++)
+    if (t->nodes[i].external_id == ext_id) return i;
+  return 0;
+}
+
+void k2o_taxonomy_free(k2o_taxonomy *t) {
+  free(t->nodes);
+  free(t->name_data);
+  free(t->rank_data);
+  memset(t, 0, sizeof *t);
+}
+
+int k2o_taxonomy_build(k2o_taxonomy *out, size_t n, const uint64_t *ext_ids,
+                       const uint64_t *parent_ext_ids, const char *const *names,
+                       const char *const *ranks) {
+  /* BFS from the root so that internal parent id < child id, children of a
+   * node contiguous (first_child/child_count), internal ids from 1. */
+  memset(out, 0, sizeof *out);
+  size_t root = n, i, j;
+  for (i = 0; i < n; i++)
+    if (parent_ext_ids[i] == ext_ids[i] || parent_ext_ids[i] == 0) {
+      root = i;
+      break;
+    }
+  if (root == n) return -1;
+  size_t *order = (size_t *)malloc(sizeof(size_t) * (n + 1));
+  uint64_t *internal_of = (uint64_t *)calloc(n, sizeof(uint64_t));
+  out->nodes = (k2o_taxonomy_node *)calloc(n + 1, sizeof(k2o_taxonomy_node));
+  if (!order || !internal_of || !out->nodes) return -1;
+  size_t head = 0, tail = 0;
+  order[tail++] = root;
+  internal_of[root] = 1;
+  uint64_t next_id = 2;
+  while (head < tail) {
+    size_t cur = order[head++];
+    uint64_t cur_id = internal_of[cur];
+    out->nodes[cur_id].external_id = ext_ids[cur];
+    out->nodes[cur_id].first_child = 0;
+    for (j = 0; j < n; j++) {
+      if (j == cur || j == root) continue;
+      if (parent_ext_ids[j] == ext_ids[cur] && !internal_of[j]) {
+        internal_of[j] = next_id;
+        if (!out->nodes[cur_id].child_count) out->nodes[cur_id].first_child = next_id;
+        out->nodes[cur_id].child_count++;
+        out->nodes[next_id].parent_id = cur_id;
+        order[tail++] = j;
+        next_id++;
+      }
+    }
+  }
+  out->node_count = next_id;
+  /* names / ranks */
+  size_t nlen = 0, rlen = 0;
+  for (i = 0; i < n; i++) {
+    nlen += strlen(names ? names[i] : "") + 1;
+    rlen += strlen(ranks ? ranks[i] : "") + 1;
+  }
+  out->name_data = (char *)calloc(nlen + 1, 1);
+  out->rank_data = (char *)calloc(rlen + 1, 1);
+  size_t no = 0, ro = 0;
+  for (i = 0; i < tail; i++) {
+    size_t src = order[i];
+    uint64_t id = internal_of[src];
+    const char *nm = names ? names[src] : "";
+    const char *rk = ranks ? ranks[src] : "";
+    out->nodes[id].name_offset = no;
+    memcpy(out->name_data + no, nm, strlen(nm) + 1);
+    no += strlen(nm) + 1;
+    out->nodes[id].rank_offset = ro;
+    memcpy(out->rank_data + ro, rk, strlen(rk) + 1);
+    ro += strlen(rk) + 1;
+  }
+  out->name_data_len = no;
+  out->rank_data_len = ro;
+  free(order);
+  free(internal_of);
+  return 0;
+}
+
+/* ------------------------------------------------------------------ */
+/* on-disk formats                                 */
+
+int k2o_load_opts(const char *path, k2o_index_options *out) {
+  FILE *f = fopen(path, "rb");
+  if (!f) return -1;
+  memset(out, 0, sizeof *out);
+  size_t n = fread(out, 1, sizeof *out, f); /* older DBs are shorter */
+  fclose(f);
+  return n >= 32 ? 0 : -1;
+}
+
+int k2o_save_opts(const char *path, const k2o_index_options *o) {
+  FILE *f = fopen(path, "wb");
+  if (!f) return -1;
+  size_t n = fwrite(o, 1, sizeof *o, f);
+  fclose(f);
+  return n == sizeof *o ? 0 : -1;
+}
+
+int k2o_load_taxonomy(const char *path, k2o_taxonomy *out) {
+  FILE *f = fopen(path, "rb");
+  if (!f) return -1;
+  char magic[8];
+  memset(out, 0, sizeof *out);
+  if (fread(magic, 1, 8, f) != 8 || memcmp(magic, "K2TAXDAT", 8)) goto bad;
+  if (fread(&out->node_count, 8, 1, f) != 1) goto bad;
+  if (fread(&out->name_data_len, 8, 1, f) != 1) goto bad;
+  if (fread(&out->rank_data_len, 8, 1, f) != 1) goto bad;
+  out->nodes = (k2o_taxonomy_node *)malloc(sizeof(k2o_taxonomy_node) * out->node_count);
+  out->name_data = (char *)malloc(out->name_data_len + 1);
+  out->rank_data = (char *)malloc(out->rank_data_len + 1);
+  if (!out->nodes || !out->name_data || !out->rank_data) goto bad;
+  if (fread(out->nodes, sizeof(k2o_taxonomy_node), out->node_count, f) != out->node_count)
+    goto bad;
+  if (fread(out->name_data, 1, out->name_data_len, f) != out->name_data_len) goto bad;
+  if (fread(out->rank_data, 1, out->rank_data_len, f) != out->rank_data_len) goto bad;
+  fclose(f);
+  return 0;
+bad:
+  fclose(f);
+  k2o_taxonomy_free(out);
+  return -1;
+}
+
+int k2o_save_taxonomy(const char *path, const k2o_taxonomy *t) {
+  FILE *f = fopen(path, "wb");
+  if (!f) return -1;
+  int ok = fwrite("K2TAXDAT", 1, 8, f) == 8 && fwrite(&t->node_count, 8, 1, f) == 1 &&
+           fwrite(&t->name_data_len, 8, 1, f) == 1 && fwrite(&t->rank_data_len, 8, 1, f) == 1 &&
+           fwrite(t->nodes, sizeof(k2o_taxonomy_node), t->node_count, f) == t->node_count &&
+           fwrite(t->name_data, 1, t->name_data_len, f) == t->name_data_len &&
+           fwrite(t->rank_data, 1, t->rank_data_len, f) == t->rank_data_len;
+  fclose(f);
+  return ok ? 0 : -1;
+}
+
+int k2o_load_cht(const char *path, k2o_cht *out) {
+  FILE *f = fopen(path, "rb");
+  if (!f) return -1;
+  memset(out, 0, sizeof *out);
+  uint64_t hdr[4];
+  if (fread(hdr, 8, 4, f) != 4) {
+    fclose(f);
+    return -1;
+  }
+  out->capacity = hdr[0];
+  out->size = hdr[1];
+  out->key_bits = hdr[2];
+  out->value_bits = hdr[3];
+  if (out->key_bits + out->value_bits != 32 || out->capacity == 0) {
+    fclose(f);
+    return -1;
+  }
+  out->cells = (uint32_t *)malloc(sizeof(uint32_t) * out->capacity);
+  out->owns_cells = 1;
+  if (!out->cells || fread(out->cells, 4, out->capacity, f) != out->capacity) {
+    fclose(f);
+    k2o_cht_free(out);
+    return -1;
+  }
+  fclose(f);
+  return 0;
+}
+
+int k2o_save_cht(const char *path, const k2o_cht *t) {
+  FILE *f = fopen(path, "wb");
+  if (!f) return -1;
+  uint64_t hdr[4] = {t->capacity, t->size, t->key_bits, t->value_bits};
+  int ok = fwrite(hdr, 8, 4, f) == 4 && fwrite(t->cells, 4, t->capacity, f) == t->capacity;
+  fclose(f);
+  return ok ? 0 : -1;
+}
+
+/* ------------------------------------------------------------------ */
+/* classify.cc: hit_counts, ResolveTree, ClassifySequence */
+
+static void hc_add(k2o_hit_counts *hc, uint64_t taxon, uint32_t n) {
+  size_t i;
+  for (i = 0; i < hc->n; i++)
+    if (hc->taxon[i] == taxon) {
+      hc->count[i] += n;
+      return;
+    }
+  if (hc->n == hc->cap) {
+    hc->cap = hc->cap ? hc->cap * 2 : 16;
+    hc->taxon = (uint64_t *)realloc(hc->taxon, hc->cap * sizeof(uint64_t));
+    hc->count = (uint32_t *)realloc(hc->count, hc->cap * sizeof(uint32_t));
+  }
+  hc->taxon[hc->n] = taxon;
+  hc->count[hc->n] = n;
+  hc->n++;
+}
+
+static uint32_t hc_get(const k2o_hit_counts *hc, uint64_t taxon) {
+  size_t i;
+  for (i = 0; i < hc->n; i++)
+    if (hc->taxon[i] == taxon) return hc->count[i];
+  return 0;
+}
+
+uint64_t k2o_resolve_tree(k2o_hit_counts *hc, const k2o_taxonomy *tax, uint64_t total_kmers,
+                          double confidence) {
+  uint64_t max_taxon = 0;
+  uint32_t max_score = 0;
+  uint32_t required_score = (uint32_t)ceil(confidence * (double)total_kmers);
+  size_t i, j;
+  /* root-to-leaf path score of every hit taxon; ties fold to the LCA */
+  for (i = 0; i < hc->n; i++) {
+    uint64_t taxon = hc->taxon[i];
+    uint32_t score = 0;
+    for (j = 0; j < hc->n; j++)
+      if (k2o_is_a_ancestor_of_b(tax, hc->taxon[j], taxon)) score += hc->count[j];
+    if (score > max_score) {
+      max_score = score;
+      max_taxon = taxon;
+    } else if (score == max_score) {
+      max_taxon = k2o_lca(tax, max_taxon, taxon);
+    }
+  }
+  /* only hits at the called taxon itself */
+  max_score = hc_get(hc, max_taxon);
+  /* walk up until the clade holds the required share of k-mers */
+  while (max_taxon && max_score < required_score) {
+    max_score = 0;
+    for (i = 0; i < hc->n; i++)
+      if (k2o_is_a_ancestor_of_b(tax, max_taxon, hc->taxon[i])) max_score += hc->count[i];
+    if (max_score >= required_score) return max_taxon;
+    max_taxon = tax->nodes[max_taxon].parent_id;
+  }
+  return max_taxon;
+}
+
+void k2o_classify_sequence(const k2o_db *db, k2o_scanner *scanner, k2o_hit_counts *hc,
+                           const char *seq1, size_t len1, const char *seq2, size_t len2,
+                           int paired, k2o_read_result *res, uint64_t **taxa_out,
+                           size_t *taxa_n) {
+  uint64_t *taxa = NULL;
+  size_t ntaxa = 0, captaxa = 0;
+  int keep_taxa = taxa_out != NULL;
+  int64_t minimizer_hit_groups = 0;
+  uint64_t lookups = 0, cells = 0, sectors = 0;
+  hc->n = 0;
+  int mate;
+  for (mate = 0; mate < 2; mate++) {
+    if (mate == 1 && !paired) break;
+    k2o_scanner_load(scanner, mate == 0 ? seq1 : seq2, mate == 0 ? len1 : len2);
+    uint64_t last_minimizer = UINT64_MAX;
+    uint64_t last_taxon = K2O_TAXID_MAX;
+    uint64_t *mp;
+    while ((mp = k2o_scanner_next(scanner)) != NULL) {
+      uint64_t taxon;
+      if (k2o_scanner_is_ambiguous(scanner)) {
+        taxon = K2O_AMBIGUOUS_SPAN_TAXON;
+      } else {
+        if (*mp != last_minimizer) {
+          int skip_lookup = 0;
+          if (db->opts->minimum_acceptable_hash_value)
+            if (k2o_fmix64(*mp) < db->opts->minimum_acceptable_hash_value) skip_lookup = 1;
+          taxon = 0;
+          if (!skip_lookup) {
+            taxon = k2o_cht_get_stats(db->cht, *mp, &cells, &sectors);
+            lookups++;
+          }
+          last_taxon = taxon;
+          last_minimizer = *mp;
+          if (taxon) minimizer_hit_groups++;
+        } else {
+          taxon = last_taxon;
+        }
+        if (taxon) hc_add(hc, taxon, 1);
+      }
+      if (keep_taxa) {
+        if (ntaxa == captaxa) {
+          captaxa = captaxa ? captaxa * 2 : 256;
+          taxa = (uint64_t *)realloc(taxa, captaxa * sizeof(uint64_t));
+        }
+        taxa[ntaxa] = taxon;
+      }
+      ntaxa++;
+    }
+    if (paired && mate == 0) {
+      if (keep_taxa) {
+        if (ntaxa == captaxa) {
+          captaxa = captaxa ? captaxa * 2 : 256;
+          taxa = (uint64_t *)realloc(taxa, captaxa * sizeof(uint64_t));
+        }
+        taxa[ntaxa] = K2O_MATE_PAIR_BORDER_TAXON;
+      }
+      ntaxa++;
+    }
+  }
+  uint64_t total_kmers = ntaxa;
+  if (paired) total_kmers--; /* the mate pair marker */
+  uint64_t call = k2o_resolve_tree(hc, db->tax, total_kmers, db->confidence);
+  /* void a call made by too few minimizer groups */
+  if (call && minimizer_hit_groups < db->minimum_hit_groups) call = 0;
+  res->call = call;
+  res->ext_call = call ? db->tax->nodes[call].external_id : 0;
+  res->total_kmers = total_kmers;
+  res->hit_groups = minimizer_hit_groups;
+  res->lookups = lookups;
+  res->cells = cells;
+  res->sectors = sectors;
+  if (keep_taxa) {
+    *taxa_out = taxa;
+    *taxa_n = ntaxa;
+  }
+}
+
+int k2o_classify_batch(const k2o_db *db, const uint8_t *bases, const uint64_t *offsets,
+                       uint64_t n_units, int paired, int threads, uint32_t *out_call_internal,
+                       uint32_t *out_call_ext, uint32_t *out_total_kmers,
+                       uint32_t *out_hit_groups, uint64_t *out_totals) {
+  uint64_t tot_lookups = 0, tot_cells = 0, tot_sectors = 0;
+  int failed = 0;
+#ifdef _OPENMP
+  if (threads <= 0) threads = omp_get_max_threads();
+#else
+  (void)threads;
+#endif
+#pragma omp parallel num_threads(threads) reduction(+ : tot_lookups, tot_cells, tot_sectors)
+  {
+    k2o_scanner sc;
+    k2o_hit_counts hc;
+    memset(&hc, 0, sizeof hc);
+    int ok = k2o_scanner_init(&sc, (int64_t)db->opts->k, (int64_t)db->opts->l,
+                              db->opts->spaced_seed_mask, db->opts->dna_db,
+                              db->opts->toggle_mask, db->opts->revcom_version) == 0;
+    if (!ok) {
+#pragma omp atomic write
+      failed = 1;
+    }
+    int64_t u;
+#pragma omp for schedule(dynamic, 256)
+    for (u = 0; u < (int64_t)n_units; u++) {
+      if (!ok) continue;
+      k2o_read_result r;
+      uint64_t s1 = paired ? 2 * (uint64_t)u : (uint64_t)u;
+      const char *p1 = (const char *)bases + offsets[s1];
+      size_t l1 = offsets[s1 + 1] - offsets[s1];
+      const char *p2 = NULL;
+      size_t l2 = 0;
+      if (paired) {
+        p2 = (const char *)bases + offsets[s1 + 1];
+        l2 = offsets[s1 + 2] - offsets[s1 + 1];
+      }
+      k2o_classify_sequence(db, &sc, &hc, p1, l1, p2, l2, paired, &r, NULL, NULL);
+      if (out_call_internal) out_call_internal[u] = (uint32_t)r.call;
+      if (out_call_ext) out_call_ext[u] = (uint32_t)r.ext_call;
+      if (out_total_kmers) out_total_kmers[u] = (uint32_t)r.total_kmers;
+      if (out_hit_groups) out_hit_groups[u] = (uint32_t)r.hit_groups;
+      tot_lookups += r.lookups;
+      tot_cells += r.cells;
+      tot_sectors += r.sectors;
+    }
+    if (ok) k2o_scanner_free(&sc);
+    free(hc.taxon);
+    free(hc.count);
+  }
+  if (out_totals) {
+    out_totals[0] = tot_lookups;
+    out_totals[1] = tot_cells;
+    out_totals[2] = tot_sectors;
+  }
+  return failed ? -1 : 0;
+}
+
+/* classify.cc AddHitlistString */
+char *k2o_hitlist_string(const k2o_taxonomy *tax, const uint64_t *taxa, size_t n) {
+  size_t cap = 64 + n * 24, len = 0;
+  char *s = (char *)malloc(cap);
+  if (!s) return NULL;
+  if (n == 0) {
+    strcpy(s, "0:0");
+    return s;
+  }
+  uint64_t last_code = taxa[0];
+  uint64_t code_count = 1;
+  size_t i;
+  for (i = 1; i <= n; i++) {
+    if (i < n && taxa[i] == last_code) {
+      code_count++;
+      continue;
+    }
+    const char *sep = i < n ? " " : "";
+    if (last_code == K2O_MATE_PAIR_BORDER_TAXON)
+      len += (size_t)sprintf(s + len, "|:|%s", sep);
+    else if (last_code == K2O_READING_FRAME_BORDER_TAXON)
+      len += (size_t)sprintf(s + len, "-:-%s", sep);
+    else if (last_code == K2O_AMBIGUOUS_SPAN_TAXON)
+      len += (size_t)sprintf(s + len, "A:%llu%s", (unsigned long long)code_count, sep);
+    else
+      len += (size_t)sprintf(s + len, "%llu:%llu%s",
+                             (unsigned long long)tax->nodes[last_code].external_id,
+                             (unsigned long long)code_count, sep);
+    if (i < n) {
+      code_count = 1;
+      last_code = taxa[i];
+    }
+  }
+  return s;
+}
+
+/* build_db.cc ProcessSequence */
+int k2o_build_add_sequence(k2o_cht *t, const k2o_taxonomy *tax, const k2o_index_options *o,
+                           const char *seq, size_t len, uint32_t taxon) {
+  k2o_scanner sc;
+  if (k2o_scanner_init(&sc, (int64_t)o->k, (int64_t)o->l, o->spaced_seed_mask, o->dna_db,
+                       o->toggle_mask, o->revcom_version))
+    return -1;
+  k2o_scanner_load(&sc, seq, len);
+  uint64_t *m;
+  int rc = 0;
+  while ((m = k2o_scanner_next(&sc)) != NULL) {
+    if (k2o_scanner_is_ambiguous(&sc)) continue;
+    if (o->minimum_acceptable_hash_value &&
+        k2o_fmix64(*m) < o->minimum_acceptable_hash_value)
+      continue;
+    if (k2o_cht_insert_lca(t, tax, *m, taxon)) {
+      rc = -1;
+      break;
+    }
+  }
+  k2o_scanner_free(&sc);
+  return rc;
+}

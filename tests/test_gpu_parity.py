@@ -1,0 +1,118 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle.
+Bit-exact: integer work only.  Run on the B200 box: pytest -m gpu."""
+import numpy as np
+import pytest
+
+import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _compare_batch(oracle_db, sess, seqs, paired, conf):
+    bases, offsets = synth.pack(seqs)
+    oracle_db.confidence = conf
+    want = oracle_db.classify_batch(bases, offsets, paired=paired)
+    call, keep, st = sess.classify(bases, offsets)
+    icall, tk, hg = sess.debug_last_batch(len(call))
+    np.testing.assert_array_equal(tk, want["total_kmers"])
+    np.testing.assert_array_equal(hg, want["hit_groups"])
+    np.testing.assert_array_equal(icall, want["call"])
+    np.testing.assert_array_equal(call, want["ext"])
+    return call, keep, st, want
+
+
+def test_minimizer_positions_match_scanner(small_db, gpu_db, oracle):
+    from nohuman_b200 import Session
+    rng = np.random.default_rng(7)
+    seqs = synth.illumina_reads(small_db.genomes, 300, 150, seed=11, n_rate=0.3)
+    # ragged lengths around k, l and the tile size; N runs; lower case; junk bytes
+    for L in [0, 1, 30, 31, 34, 35, 36, 66, 123, 124, 125, 157, 158, 159, 160, 250, 283, 1000, 5000]:
+        seqs.append(synth.random_genome(rng, L))
+    s = synth.random_genome(rng, 400)
+    s[50:60] = ord("N"); s[100] = ord("n"); s[135] = ord("R"); s[200:300] |= 0x20; s[399] = 0
+    seqs.append(s)
+    s = synth.random_genome(rng, 300)
+    s[0] = ord("N"); s[34] = ord("N"); s[69] = ord("N"); s[299] = ord("N")
+    seqs.append(s)
+    seqs.append(np.full(200, ord("N"), np.uint8))
+    seqs.append(np.full(200, ord("A"), np.uint8))
+    bases, offsets = synth.pack(seqs)
+    with Session(gpu_db) as sess:
+        mins, amb, pos_off = sess.debug_minimizers(bases, offsets)
+    for i, sq in enumerate(seqs):
+        wm, wa = oracle.scan_positions(small_db.opts, bytes(sq))
+        lo, hi = int(pos_off[i]), int(pos_off[i + 1])
+        assert hi - lo == len(wm), f"seq {i} len {len(sq)}"
+        np.testing.assert_array_equal(amb[lo:hi], wa, err_msg=f"ambig seq {i} len {len(sq)}")
+        ok = wa == 0
+        np.testing.assert_array_equal(mins[lo:hi][ok], wm[ok], err_msg=f"min seq {i} len {len(sq)}")
+
+
+def test_probe_matches_get(small_db, gpu_db, oracle):
+    from nohuman_b200 import Session
+    rng = np.random.default_rng(3)
+    present = []
+    for _, g in small_db.genomes:
+        m, a = oracle.scan_positions(small_db.opts, bytes(g[:20000]))
+        present.append(m[a == 0])
+    keys = np.concatenate(present + [rng.integers(0, 1 << 62, size=50000, dtype=np.uint64)])
+    with Session(gpu_db) as sess:
+        got = sess.debug_probe(keys)
+    want = np.array([small_db.get(int(k)) for k in keys], dtype=np.uint32)
+    np.testing.assert_array_equal(got, want)
+    assert (want != 0).sum() > 10000
+
+
+@pytest.mark.parametrize("conf", [0.0, 0.1, 0.5, 1.0])
+def test_single_end_matches_oracle(small_db, gpu_db, conf):
+    from nohuman_b200 import Session
+    seqs = synth.illumina_reads(small_db.genomes, 4000, 150, seed=2)
+    with Session(gpu_db, confidence=conf) as sess:
+        call, keep, st, want = _compare_batch(small_db, sess, seqs, False, conf)
+    np.testing.assert_array_equal(keep, (call == 0).astype(np.uint8))
+    assert st.n_classified == int((want["call"] != 0).sum())
+    assert st.n_units == 4000
+    assert st.n_lookups == want["lookups"]  # 150 bp reads are single-tile: exact
+
+
+@pytest.mark.parametrize("conf,keep_human", [(0.0, False), (0.5, False), (0.5, True)])
+def test_paired_end_matches_oracle(small_db, gpu_db, conf, keep_human):
+    from nohuman_b200 import Session
+    seqs = synth.illumina_reads(small_db.genomes, 3000, 150, seed=3, paired=True)
+    with Session(gpu_db, confidence=conf, paired=True, keep_human=keep_human) as sess:
+        call, keep, st, want = _compare_batch(small_db, sess, seqs, True, conf)
+    cls = (call != 0).astype(np.uint8)
+    np.testing.assert_array_equal(keep, cls if keep_human else 1 - cls)
+    assert st.n_kept == int(keep.sum())
+
+
+def test_long_reads_match_oracle(small_db, gpu_db):
+    from nohuman_b200 import Session
+    seqs = synth.ont_reads(small_db.genomes, 300, seed=4, n50=4000, max_len=30000)
+    with Session(gpu_db, confidence=0.05, keep_human=True) as sess:
+        _compare_batch(small_db, sess, seqs, False, 0.05)
+
+
+def test_edge_cases(small_db, gpu_db):
+    from nohuman_b200 import Session
+    rng = np.random.default_rng(5)
+    g = small_db.genomes[0][1]
+    seqs = [np.zeros(0, np.uint8), g[:34].copy(), g[:35].copy(), g[100:136].copy(),
+            np.full(150, ord("N"), np.uint8), np.full(150, ord("A"), np.uint8)]
+    r = g[1000:1150].copy(); r[75] = ord("N"); seqs.append(r)
+    r = g[2000:2300].copy(); r[::40] = ord("N"); seqs.append(r)
+    r = g[3000:3150].copy(); r |= 0x20; seqs.append(r)
+    seqs += [synth.random_genome(rng, int(L)) for L in rng.integers(0, 400, size=200)]
+    with Session(gpu_db) as sess:
+        _compare_batch(small_db, sess, seqs, False, 0.0)
+        # empty batch
+        call, keep, st = sess.classify(np.zeros(0, np.uint8), np.zeros(1, np.uint64))
+        assert len(call) == 0 and st.n_units == 0
+    # paired with ragged mates (one mate shorter than k)
+    pseqs = []
+    for i in range(100):
+        a = g[i * 500:i * 500 + 150].copy()
+        b = synth.revcomp(g[i * 500 + 200:i * 500 + 350]) if i % 3 else g[:20].copy()
+        pseqs += [a, b]
+    with Session(gpu_db, paired=True, confidence=0.2) as sess:
+        _compare_batch(small_db, sess, pseqs, True, 0.2)
