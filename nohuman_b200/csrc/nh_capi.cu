@@ -258,6 +258,40 @@ extern "C" int nh_db_open_memory(const void *opts, size_t opts_len, const void *
   return NH_OK;
 }
 
+/* Zeroed table of `capacity` cells for the synthetic builder (nh_synth.cu);
+ * value_bits as build_db.cc picks it: the smallest b with 2^b >= node_count. */
+int nh_db_create_empty(const void *opts, size_t opts_len, const void *taxo, size_t taxo_len,
+                       uint64_t capacity, int device, nh_db **out) {
+  int rc = select_device(device);
+  if (rc) return rc;
+  nh_db *db = new nh_db();
+  db->info.device = device;
+  rc = parse_opts_taxo(db, opts, opts_len, taxo, taxo_len);
+  if (rc) {
+    delete db;
+    return rc;
+  }
+  uint64_t vb = 1;
+  while ((1ULL << vb) < db->info.node_count) vb++;
+  const size_t bytes = ((capacity + 7) / 8) * 32;
+  cudaError_t e = cudaMalloc(&db->d_cells, bytes);
+  if (e != cudaSuccess) {
+    delete db;
+    return nh_set_error(NH_ERR_NOMEM, "cudaMalloc(%zu) for the hash table failed: %s", bytes,
+                        cudaGetErrorString(e));
+  }
+  db->owns_cells = true;
+  cudaMemset(db->d_cells, 0, bytes);
+  const uint64_t hdr[4] = {capacity, 0, 32 - vb, vb};
+  rc = finish_db(db, hdr);
+  if (rc) {
+    nh_db_close(db);
+    return rc;
+  }
+  *out = db;
+  return NH_OK;
+}
+
 extern "C" int nh_db_open(const char *db_dir, int device, nh_db **out) {
   if (!db_dir || !out) return nh_set_error(NH_ERR_INVALID, "null argument");
   std::string dir;
@@ -266,8 +300,10 @@ extern "C" int nh_db_open(const char *db_dir, int device, nh_db **out) {
   rc = select_device(device);
   if (rc) return rc;
   std::vector<uint8_t> opts, taxo;
-  if ((rc = read_file(dir + "/opts.k2d", opts, 64))) return rc;
-  if ((rc = read_file(dir + "/taxo.k2d", taxo, (size_t)-1))) return rc;
+  rc = read_file(dir + "/opts.k2d", opts, 64);
+  if (rc) return rc;
+  rc = read_file(dir + "/taxo.k2d", taxo, (size_t)-1);
+  if (rc) return rc;
   /* hash.k2d: 32-byte header, then capacity x u32; streamed through a pinned
    * staging buffer so that the multi-GB table never needs a second host copy */
   std::string hp = dir + "/hash.k2d";
