@@ -38,7 +38,7 @@ def test_oracle_reproduces_fixture(oracle, golden, golden_db_dir, name, paired, 
     for f in ("ext", "call", "hit_groups", "total_kmers"):
         np.testing.assert_array_equal(r[f], golden[f"{t}_{f}"], err_msg=f)
     assert r["lookups"] == int(golden[f"{t}_lookups"][0])
-    assert (r["ext"] != 0).any() and (r["ext"] == 0).any()
+    assert (r["ext"] != 0).any() and (name == "ont" or (r["ext"] == 0).any())
 
 
 def test_oracle_reproduces_minimizer_stream_and_hitlists(oracle, golden, golden_db_dir):
