@@ -84,10 +84,13 @@ typedef struct {
   uint64_t n_bases;
   uint64_t n_tiles;        /* minimizer-kernel work items */
   uint64_t n_lookups;      /* hash-table probes issued */
-  float ms_plan, ms_minimizer, ms_probe, ms_score; /* device time per stage (CUDA events) */
+  /* device time per stage (CUDA events).  With fused_kernel = 1 the scan, the
+   * probe and the scoring of short units are ONE kernel timed as ms_minimizer
+   * (ms_probe = 0) and ms_score covers only the units left to k_score. */
+  float ms_plan, ms_minimizer, ms_probe, ms_score;
   float ms_h2d, ms_d2h;
   uint32_t gpu_launches;   /* kernels launched for this batch */
-  uint32_t reserved;
+  uint32_t fused_kernel;   /* 1: k_scan_probe_score path, 0: warp-per-tile kernels */
 } nh_batch_stats_t;
 
 typedef struct {

@@ -56,7 +56,7 @@ class BatchStats(C.Structure):
         ("n_lookups", C.c_uint64),
         ("ms_plan", C.c_float), ("ms_minimizer", C.c_float), ("ms_probe", C.c_float),
         ("ms_score", C.c_float), ("ms_h2d", C.c_float), ("ms_d2h", C.c_float),
-        ("gpu_launches", C.c_uint32), ("reserved", C.c_uint32),
+        ("gpu_launches", C.c_uint32), ("fused_kernel", C.c_uint32),
     ]
 
     def as_dict(self):

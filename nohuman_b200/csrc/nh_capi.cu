@@ -430,6 +430,11 @@ extern "C" int nh_session_create(nh_db *db, const nh_params_t *params, nh_sessio
   if (params->paired) ms += ms & 1;
   s->cap_bases = mb;
   s->cap_seqs = ms;
+  {
+    /* NH_LEGACY_KERNELS=1 forces the warp-per-tile kernels (A/B runs, generic window widths) */
+    const char *legacy = getenv("NH_LEGACY_KERNELS");
+    s->use_fused = nh_fused_supported(db->params) && !(legacy && legacy[0] == '1');
+  }
   const NhDbParams &P = db->params;
   /* every sequence has at most ceil(positions / tile_pos) tiles */
   s->cap_tiles = ms + mb / (uint64_t)P.tile_pos + 1;
@@ -454,6 +459,7 @@ extern "C" int nh_session_create(nh_db *db, const nh_params_t *params, nh_sessio
   ALLOC(s->d_dbg_total, ms);
   ALLOC(s->d_dbg_groups, ms);
   ALLOC(s->d_overflow, ms);
+  ALLOC(s->d_deferred, ms);
   ALLOC(s->d_counters, 1);
 #undef ALLOC
   if (e == cudaSuccess) e = cudaHostAlloc(&s->h_counters, sizeof(NhCounters), cudaHostAllocDefault);
@@ -490,6 +496,7 @@ extern "C" void nh_session_destroy(nh_session *s) {
   cudaFree(s->d_dbg_total);
   cudaFree(s->d_dbg_groups);
   cudaFree(s->d_overflow);
+  cudaFree(s->d_deferred);
   cudaFree(s->d_counters);
   if (s->h_counters) cudaFreeHost(s->h_counters);
   for (int i = 0; i < NH_NUM_EVENTS; i++)
@@ -556,17 +563,26 @@ static int enqueue_batch(nh_session *s, const uint8_t *d_bases, const uint64_t *
   int launches = 0;
   cudaStream_t st = s->stream;
   cudaEventRecord(s->ev[EV_PLAN0], st);
+  const bool fused = s->use_fused;
+  B.deferred_units = fused ? s->d_deferred : nullptr;
   launches += nh_launch_plan(P, B, st);
   cudaEventRecord(s->ev[EV_MIN0], st);
-  launches += nh_launch_minimizers(P, B, (uint32_t)tiles_upper, sm, st);
-  cudaEventRecord(s->ev[EV_PROBE0], st);
-  launches += nh_launch_probe(P, s->d_lk_min, s->d_lk_taxon, &s->d_counters->n_lookups,
-                              (uint32_t)lookups_upper, sm, st);
+  if (fused) {
+    /* scan + probe + in-warp scoring of short units in one kernel; ms_probe reads 0 */
+    launches += nh_launch_fused(P, B, SP, (uint32_t)tiles_upper, sm, st);
+    cudaEventRecord(s->ev[EV_PROBE0], st);
+  } else {
+    launches += nh_launch_minimizers(P, B, (uint32_t)tiles_upper, sm, st);
+    cudaEventRecord(s->ev[EV_PROBE0], st);
+    launches += nh_launch_probe(P, s->d_lk_min, s->d_lk_taxon, &s->d_counters->n_lookups,
+                                (uint32_t)lookups_upper, sm, st);
+  }
   cudaEventRecord(s->ev[EV_SCORE0], st);
   launches += nh_launch_score(P, B, SP, sm, st);
   cudaEventRecord(s->ev[EV_SCORE1], st);
   cudaMemcpyAsync(s->h_counters, s->d_counters, sizeof(NhCounters), cudaMemcpyDeviceToHost, st);
   s->last_launches = (uint32_t)launches;
+  s->last_fused = fused;
   s->last_units = B.n_units;
   s->last_bases = total_bases;
   s->pending = true;
@@ -613,6 +629,7 @@ extern "C" int nh_session_sync(nh_session *s, nh_batch_stats_t *stats) {
         cudaEventElapsedTime(&stats->ms_d2h, s->ev[EV_SCORE1], s->ev[EV_D2H1]);
       }
       stats->gpu_launches = s->last_launches;
+      stats->fused_kernel = s->last_fused ? 1u : 0u;
     }
   }
   return NH_OK;

@@ -42,7 +42,7 @@ struct nh_session {
   uint8_t *d_bases = nullptr;
   uint64_t *d_offsets = nullptr;
   uint32_t *d_tile_base = nullptr;
-  uint32_t *d_block_sums = nullptr;
+  uint64_t *d_block_sums = nullptr;
   NhTile *d_tiles = nullptr;
   NhTileOut *d_tile_out = nullptr;
   uint64_t *d_lk_min = nullptr;
@@ -52,6 +52,8 @@ struct nh_session {
   uint8_t *d_out_keep = nullptr;
   uint32_t *d_dbg_call = nullptr, *d_dbg_total = nullptr, *d_dbg_groups = nullptr;
   uint32_t *d_overflow = nullptr;
+  uint32_t *d_deferred = nullptr;
+  bool use_fused = false, last_fused = false;
   NhCounters *d_counters = nullptr;
   NhCounters *h_counters = nullptr; /* pinned */
   cudaStream_t stream = nullptr;

@@ -30,32 +30,33 @@ __device__ __forceinline__ uint32_t warp_sum_u32(uint32_t v) {
   return __reduce_add_sync(FULL_MASK, v);
 }
 
-/* exclusive scan over a block of up to 1024 threads; *total gets the sum */
-__device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t *total,
-                                                    uint32_t *s_warp /* [33] */) {
+/* exclusive scan over a block of up to 1024 threads; *total gets the sum.
+ * The plan scans (tiles << 32 | k-mer positions) in one pass. */
+__device__ __forceinline__ uint64_t block_excl_scan(uint64_t v, uint64_t *total,
+                                                    uint64_t *s_warp /* [33] */) {
   uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
-  uint32_t inc = v;
+  uint64_t inc = v;
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) {
-    uint32_t o = __shfl_up_sync(FULL_MASK, inc, d);
+    uint64_t o = __shfl_up_sync(FULL_MASK, inc, d);
     if (lane >= (uint32_t)d) inc += o;
   }
   if (lane == 31) s_warp[warp] = inc;
   __syncthreads();
   if (warp == 0) {
     uint32_t nw = (blockDim.x + 31) >> 5;
-    uint32_t ws = lane < nw ? s_warp[lane] : 0;
-    uint32_t winc = ws;
+    uint64_t ws = lane < nw ? s_warp[lane] : 0;
+    uint64_t winc = ws;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-      uint32_t o = __shfl_up_sync(FULL_MASK, winc, d);
+      uint64_t o = __shfl_up_sync(FULL_MASK, winc, d);
       if (lane >= (uint32_t)d) winc += o;
     }
     s_warp[lane] = winc - ws; /* exclusive warp base */
     if (lane == 31) s_warp[32] = winc;
   }
   __syncthreads();
-  uint32_t r = s_warp[warp] + inc - v;
+  uint64_t r = s_warp[warp] + inc - v;
   *total = s_warp[32];
   __syncthreads();
   return r;
@@ -66,69 +67,101 @@ __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t *total,
 
 #define PLAN_THREADS 1024
 
-__device__ __forceinline__ uint32_t seq_ntiles(const uint64_t *__restrict__ off, uint32_t s,
-                                               int k, int tile_pos) {
+__device__ __forceinline__ uint32_t seq_npos(const uint64_t *__restrict__ off, uint32_t s, int k) {
   uint64_t len = off[s + 1] - off[s];
-  if (len < (uint64_t)k) return 0;
-  uint64_t npos = len - (uint64_t)k + 1;
-  return (uint32_t)((npos + (uint64_t)tile_pos - 1) / (uint64_t)tile_pos);
+  return len < (uint64_t)k ? 0u : (uint32_t)(len - (uint64_t)k + 1);
+}
+
+__device__ __forceinline__ uint32_t npos_ntiles(uint32_t npos, int tile_pos) {
+  return (npos + (uint32_t)tile_pos - 1u) / (uint32_t)tile_pos;
+}
+
+/* (tiles << 32) | positions of sequence s */
+__device__ __forceinline__ uint64_t seq_work(const uint64_t *__restrict__ off, uint32_t s, int k,
+                                             int tile_pos) {
+  const uint32_t np = seq_npos(off, s, k);
+  return ((uint64_t)npos_ntiles(np, tile_pos) << 32) | np;
 }
 
 __global__ void __launch_bounds__(PLAN_THREADS)
 k_plan_count(const uint64_t *__restrict__ off, uint32_t n_seqs, int k, int tile_pos,
-             uint32_t *__restrict__ block_sums) {
-  __shared__ uint32_t s_warp[33];
+             uint64_t *__restrict__ block_sums) {
+  __shared__ uint64_t s_warp[33];
   uint32_t s = blockIdx.x * PLAN_THREADS + threadIdx.x;
-  uint32_t v = s < n_seqs ? seq_ntiles(off, s, k, tile_pos) : 0;
-  uint32_t total;
+  uint64_t v = s < n_seqs ? seq_work(off, s, k, tile_pos) : 0;
+  uint64_t total;
   block_excl_scan(v, &total, s_warp);
   if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
 }
 
 /* single block: exclusive scan of the per-block sums, reset of the batch counters */
 __global__ void __launch_bounds__(PLAN_THREADS)
-k_plan_scan(uint32_t *__restrict__ block_sums, uint32_t nb, NhCounters *__restrict__ counters) {
-  __shared__ uint32_t s_warp[33];
-  __shared__ uint32_t s_running;
+k_plan_scan(uint64_t *__restrict__ block_sums, uint32_t nb, NhCounters *__restrict__ counters) {
+  __shared__ uint64_t s_warp[33];
+  __shared__ uint64_t s_running;
   if (threadIdx.x == 0) s_running = 0;
   __syncthreads();
   for (uint32_t base = 0; base < nb; base += PLAN_THREADS) {
     uint32_t i = base + threadIdx.x;
-    uint32_t v = i < nb ? block_sums[i] : 0;
-    uint32_t total;
-    uint32_t ex = block_excl_scan(v, &total, s_warp);
-    uint32_t run = s_running;
+    uint64_t v = i < nb ? block_sums[i] : 0;
+    uint64_t total;
+    uint64_t ex = block_excl_scan(v, &total, s_warp);
+    uint64_t run = s_running;
     if (i < nb) block_sums[i] = run + ex;
     __syncthreads();
     if (threadIdx.x == 0) s_running = run + total;
     __syncthreads();
   }
   if (threadIdx.x == 0) {
-    counters->n_tiles = s_running;
+    counters->n_tiles = (uint32_t)(s_running >> 32);
     counters->n_lookups = 0;
     counters->n_classified = 0;
     counters->n_kept = 0;
     counters->n_overflow = 0;
     counters->error = 0;
+    counters->n_deferred = 0;
   }
 }
 
+/* Writes the tile descriptors.  With `fused` set it also decides, per unit,
+ * whether the fused kernel can score it inside one warp (every mate at most
+ * one tile, both tiles in the same group of 32) and queues the other units
+ * for k_score. */
 __global__ void __launch_bounds__(PLAN_THREADS)
-k_plan_fill(const uint64_t *__restrict__ off, uint32_t n_seqs, int k, int tile_pos,
-            const uint32_t *__restrict__ block_sums, uint32_t *__restrict__ tile_base,
-            NhTile *__restrict__ tiles, const NhCounters *__restrict__ counters) {
-  __shared__ uint32_t s_warp[33];
+k_plan_fill(const uint64_t *__restrict__ off, uint32_t n_seqs, int k, int tile_pos, int paired,
+            int fused, const uint64_t *__restrict__ block_sums, uint32_t *__restrict__ tile_base,
+            NhTile *__restrict__ tiles, uint32_t *__restrict__ deferred_units,
+            NhCounters *__restrict__ counters) {
+  __shared__ uint64_t s_warp[33];
   uint32_t s = blockIdx.x * PLAN_THREADS + threadIdx.x;
-  uint32_t v = s < n_seqs ? seq_ntiles(off, s, k, tile_pos) : 0;
-  uint32_t total;
-  uint32_t ex = block_excl_scan(v, &total, s_warp);
+  uint64_t w = s < n_seqs ? seq_work(off, s, k, tile_pos) : 0;
+  uint64_t total;
+  uint64_t ex = block_excl_scan(w, &total, s_warp);
   if (s < n_seqs) {
-    uint32_t tb = block_sums[blockIdx.x] + ex;
+    const uint64_t before = block_sums[blockIdx.x] + ex;
+    const uint32_t tb = (uint32_t)(before >> 32), pb = (uint32_t)before;
+    const uint32_t v = (uint32_t)(w >> 32);
     tile_base[s] = tb;
+    uint32_t role = NH_ROLE_DEFERRED;
+    if (fused) {
+      const uint32_t mate = paired ? (s & 1u) : 0u;
+      const uint32_t v_other = paired ? npos_ntiles(seq_npos(off, s ^ 1u, k), tile_pos) : 0u;
+      bool simple = v <= 1u && v_other <= 1u && v + v_other >= 1u;
+      if (v == 1u && v_other == 1u) {
+        const uint32_t t0 = mate == 0u ? tb : tb - 1u;
+        simple = simple && (t0 & 31u) != 31u;
+      }
+      if (simple && v == 1u)
+        role = v_other == 0u ? NH_ROLE_LEADER : (mate == 0u ? NH_ROLE_LEADER2 : NH_ROLE_PARTNER);
+      if (mate == 0u && !simple)
+        deferred_units[atomicAdd(&counters->n_deferred, 1u)] = paired ? (s >> 1) : s;
+    }
     for (uint32_t t = 0; t < v; t++) {
       NhTile d;
       d.seq = s;
       d.pos_begin = t * (uint32_t)tile_pos;
+      d.slot = pb + d.pos_begin;
+      d.role = role;
       tiles[tb + t] = d;
     }
   }
@@ -540,7 +573,10 @@ k_score(const NhDbParams db, const NhBatchPtrs b, const NhScoreParams sp) {
   uint32_t *cnts = keys + NH_WARP_HASH_SLOTS;
   uint32_t classified = 0, kept = 0;
   const uint32_t wstride = gridDim.x * NH_WARPS_PER_BLOCK;
-  for (uint32_t u = blockIdx.x * NH_WARPS_PER_BLOCK + warp; u < b.n_units; u += wstride) {
+  /* fused path: only the units k_plan_fill deferred; legacy path: every unit */
+  const uint32_t n_todo = b.deferred_units ? b.counters->n_deferred : b.n_units;
+  for (uint32_t i = blockIdx.x * NH_WARPS_PER_BLOCK + warp; i < n_todo; i += wstride) {
+    const uint32_t u = b.deferred_units ? b.deferred_units[i] : i;
     if (!score_unit(db, b, sp, parent, keys, cnts, NH_WARP_HASH_SLOTS - 1u, u, lane, &classified,
                     &kept)) {
       if (lane == 0) b.overflow_units[atomicAdd(&b.counters->n_overflow, 1u)] = u;
@@ -576,6 +612,283 @@ k_score_big(const NhDbParams db, const NhBatchPtrs b, const NhScoreParams sp) {
 }
 
 /* ------------------------------------------------------------------ */
+/* fused path: scan -> probe -> score in one kernel                     */
+/*
+ * One warp takes a group of 32 consecutive tiles.
+ *   phase A  every lane scans ITS OWN tile base by base: rolling forward and
+ *            reverse-complement l-mers, canonical/seed/toggle, window minimum
+ *            over a register ring, run-length de-duplication; the distinct
+ *            minimizers go to the tile's lookup slots in global memory (they
+ *            stay in L2 for phase B).  ~1/3 of the instructions of the
+ *            warp-per-tile kernel, because nothing is recomputed per l-mer.
+ *   phase B  the group's lookups are flattened over the 32 lanes and probed
+ *            (same cht_get as k_probe), so every lane has a DRAM request in
+ *            flight while other warps of the SM are in phase A.
+ *   phase C  lanes that lead a short unit (roles from k_plan_fill) fold the
+ *            taxa of their tile (+ the mate's tile) into a per-lane table and
+ *            run ResolveTree serially; other units are left to k_score.
+ * Only the window width W is a template parameter (kraken2's default
+ * k=35,l=31 gives W=5); other databases take the warp-per-tile kernels.
+ */
+
+struct FusedWarpSmem {
+  uint32_t prefix[33];                   /* exclusive scan of lookups per tile */
+  uint32_t slot[32];                     /* first lookup slot of each tile */
+  uint32_t keys[NH_LANE_TAXA * 32];      /* [slot][lane] */
+  uint32_t cnts[NH_LANE_TAXA * 32];
+};
+
+__device__ __forceinline__ uint32_t lane_tab_get(const FusedWarpSmem &sm, uint32_t lane,
+                                                 uint32_t n, uint32_t taxon) {
+  for (uint32_t i = 0; i < n; i++)
+    if (sm.keys[i * 32u + lane] == taxon) return sm.cnts[i * 32u + lane];
+  return 0;
+}
+
+template <int W>
+__global__ void __launch_bounds__(NH_BLOCK_THREADS)
+k_scan_probe_score(const NhDbParams db, const NhBatchPtrs b, const NhScoreParams sp) {
+  extern __shared__ uint32_t s_dyn[];
+  uint32_t *s_parent = s_dyn;
+  const bool smem_parent = db.node_count <= NH_SMEM_PARENT_MAX;
+  const uint32_t parent_words = smem_parent ? db.node_count : 0u;
+  FusedWarpSmem *s_warps = reinterpret_cast<FusedWarpSmem *>(s_dyn + ((parent_words + 3u) & ~3u));
+  if (smem_parent) {
+    for (uint32_t i = threadIdx.x; i < db.node_count; i += blockDim.x) s_parent[i] = db.parent[i];
+    __syncthreads();
+  }
+  const uint32_t *parent = smem_parent ? s_parent : db.parent;
+  const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+  FusedWarpSmem &sm = s_warps[warp];
+  const uint32_t n_tiles = b.counters->n_tiles;
+  const int k = db.k, l = db.l;
+  const uint64_t lmask = (1ULL << (2 * l)) - 1ULL;
+  const uint32_t rc_shift = 2u * (uint32_t)(l - 1);
+  uint32_t tot_lookups = 0, tot_classified = 0, tot_kept = 0;
+
+  for (uint32_t group = blockIdx.x * NH_WARPS_PER_BLOCK + warp; group * 32u < n_tiles;
+       group += gridDim.x * NH_WARPS_PER_BLOCK) {
+    const uint32_t tile = group * 32u + lane;
+    const bool have = tile < n_tiles;
+    NhTile t;
+    t.seq = 0; t.pos_begin = 0; t.slot = 0; t.role = NH_ROLE_DEFERRED;
+    if (have) t = b.tiles[tile];
+
+    /* ---------------- phase A: lane-serial minimizer scan ---------------- */
+    uint32_t n_runs = 0;
+    {
+      uint64_t so = 0;
+      uint32_t nb = 0; /* bases of this lane's tile */
+      if (have) {
+        so = b.offsets[t.seq];
+        const uint32_t len = (uint32_t)(b.offsets[t.seq + 1] - so);
+        uint32_t npos = len - (uint32_t)k + 1u - t.pos_begin;
+        if (npos > (uint32_t)db.tile_pos) npos = (uint32_t)db.tile_pos;
+        nb = npos + (uint32_t)k - 1u;
+      }
+      const uint8_t *g = b.bases + so + t.pos_begin;
+      const uint32_t mis = (uint32_t)((uintptr_t)g & 15u);
+      const uint4 *q = reinterpret_cast<const uint4 *>(g - mis);
+      const uint32_t my_chunks = have ? (mis + nb + 15u) >> 4 : 0u;
+      const uint32_t max_chunks = __reduce_max_sync(FULL_MASK, my_chunks);
+
+      uint64_t fwd = 0, rc = 0;
+      uint64_t ring[W > 1 ? W - 1 : 1];
+#pragma unroll
+      for (int i = 0; i < (W > 1 ? W - 1 : 1); i++) ring[i] = NH_NONE64;
+      uint32_t c_run = 0;           /* consecutive unambiguous bases ending here */
+      uint64_t last = NH_NONE64;    /* minimizer of the open run */
+      uint32_t cnt = 0;             /* k-mer positions in the open run */
+      uint64_t *out_min = b.lk_min + t.slot;
+      uint8_t *out_cnt = b.lk_cnt + t.slot;
+      const bool dbg = b.dbg_pos_min != nullptr;
+      const uint64_t dbg_base = dbg && have ? b.dbg_pos_offsets[t.seq] + t.pos_begin : 0;
+
+      for (uint32_t ch = 0; ch < max_chunks; ch++) {
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (ch < my_chunks) v = __ldg(q + ch);
+        uint32_t a0, a1, a2, a3;
+        const uint32_t p0 = nh_pack4(v.x, &a0), p1 = nh_pack4(v.y, &a1);
+        const uint32_t p2 = nh_pack4(v.z, &a2), p3 = nh_pack4(v.w, &a3);
+        const uint32_t codes = (p0 << 24) | (p1 << 16) | (p2 << 8) | p3; /* first base in the MSBs */
+        const uint32_t ambs = a0 | (a1 << 4) | (a2 << 8) | (a3 << 12);   /* bit i = base i */
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+          const uint32_t idx = ch * 16u + (uint32_t)j - mis; /* base index in the tile (wraps when before it) */
+          if (idx < nb) {
+            const uint32_t c = (codes >> (30 - 2 * j)) & 3u;
+            const bool amb = (ambs >> j) & 1u;
+            fwd = ((fwd << 2) | c) & lmask;
+            rc = (rc >> 2) | ((uint64_t)(3u - c) << rc_shift);
+            c_run = amb ? 0u : c_run + 1u;
+            uint64_t cand = NH_NONE64;
+            if (c_run >= (uint32_t)l) {
+              const uint64_t rcv = db.revcom_version == 0
+                                       ? (((rc << (64 - 2 * l)) | ((1ULL << (64 - 2 * l)) - 1ULL)) & lmask)
+                                       : rc;
+              cand = ((fwd < rcv ? fwd : rcv) & db.seed_mask) ^ db.toggle;
+            }
+            uint64_t m = cand;
+#pragma unroll
+            for (int i = 0; i < W - 1; i++) m = min_u64(m, ring[i]);
+#pragma unroll
+            for (int i = W - 2; i > 0; i--) ring[i] = ring[i - 1];
+            if (W > 1) ring[0] = cand;
+            if (idx >= (uint32_t)(k - 1)) {
+              const bool nonamb = c_run >= (uint32_t)db.amb_span;
+              const uint64_t mz = m ^ db.toggle;
+              if (dbg) {
+                const uint64_t o = dbg_base + (idx - (uint32_t)(k - 1));
+                b.dbg_pos_min[o] = mz;
+                b.dbg_pos_ambig[o] = nonamb ? 0 : 1;
+              }
+              if (nonamb) {
+                if (mz != last) {
+                  if (cnt) {
+                    out_min[n_runs] = last;
+                    out_cnt[n_runs] = (uint8_t)cnt;
+                    n_runs++;
+                  }
+                  last = mz;
+                  cnt = 1;
+                } else {
+                  cnt++;
+                }
+              }
+            }
+          }
+        }
+      }
+      if (cnt) {
+        out_min[n_runs] = last;
+        out_cnt[n_runs] = (uint8_t)cnt;
+        n_runs++;
+      }
+      if (have) {
+        NhTileOut o;
+        o.lk_off = t.slot;
+        o.lk_cnt = n_runs;
+        b.tile_out[tile] = o;
+      }
+    }
+
+    /* ---------------- phase B: probe the group's lookups ---------------- */
+    uint32_t inc = n_runs;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t o = __shfl_up_sync(FULL_MASK, inc, d);
+      if (lane >= (uint32_t)d) inc += o;
+    }
+    const uint32_t total = __shfl_sync(FULL_MASK, inc, 31);
+    sm.prefix[lane] = inc - n_runs;
+    sm.slot[lane] = t.slot;
+    if (lane == 31) sm.prefix[32] = total;
+    __syncwarp(); /* also orders the lookup slots written above before the reads below */
+    tot_lookups += n_runs;
+    for (uint32_t e = lane; e < total; e += 32u) {
+      /* owner tile: largest o with prefix[o] <= e */
+      uint32_t o = 0;
+#pragma unroll
+      for (int step = 16; step >= 1; step >>= 1)
+        if (sm.prefix[o + step] <= e) o += (uint32_t)step;
+      const uint32_t oslot = sm.slot[o] + (e - sm.prefix[o]);
+      const uint64_t key = __ldcg(b.lk_min + oslot);
+      b.lk_taxon[oslot] = cht_get(db, key);
+    }
+    __syncwarp();
+
+    /* ---------------- phase C: score short units in the warp ---------------- */
+    const uint32_t n_next = __shfl_down_sync(FULL_MASK, n_runs, 1);
+    const uint32_t slot_next = __shfl_down_sync(FULL_MASK, t.slot, 1);
+    if (have && (t.role == NH_ROLE_LEADER || t.role == NH_ROLE_LEADER2)) {
+      uint32_t ntab = 0;
+      int groups = 0;
+      bool ok = true;
+      const uint32_t parts = t.role == NH_ROLE_LEADER2 ? 2u : 1u;
+      for (uint32_t part = 0; part < parts; part++) {
+        const uint32_t base = part ? slot_next : t.slot;
+        const uint32_t n = part ? n_next : n_runs;
+        for (uint32_t j = 0; j < n; j++) {
+          const uint32_t tx = __ldcg(b.lk_taxon + base + j);
+          if (!tx) continue;
+          groups++;
+          const uint32_t c = (uint32_t)__ldcg(b.lk_cnt + base + j);
+          uint32_t i = 0;
+          for (; i < ntab; i++)
+            if (sm.keys[i * 32u + lane] == tx) break;
+          if (i < ntab) {
+            sm.cnts[i * 32u + lane] += c;
+          } else if (ntab < NH_LANE_TAXA) {
+            sm.keys[ntab * 32u + lane] = tx;
+            sm.cnts[ntab * 32u + lane] = c;
+            ntab++;
+          } else {
+            ok = false;
+          }
+        }
+      }
+      const uint32_t u = b.paired ? (t.seq >> 1) : t.seq;
+      if (!ok) {
+        /* more distinct taxa than a lane table holds: k_score_big takes the unit */
+        b.overflow_units[atomicAdd(&b.counters->n_overflow, 1u)] = u;
+      } else {
+        const uint32_t s0 = b.paired ? (t.seq & ~1u) : t.seq;
+        uint32_t total_kmers = 0;
+        for (uint32_t mm = 0; mm < (b.paired ? 2u : 1u); mm++) {
+          const uint64_t len = b.offsets[s0 + mm + 1] - b.offsets[s0 + mm];
+          if (len >= (uint64_t)k) total_kmers += (uint32_t)(len - (uint64_t)k + 1);
+        }
+        /* ResolveTree */
+        uint32_t best_s = 0, best_t = 0;
+        for (uint32_t i = 0; i < ntab; i++) {
+          const uint32_t tx = sm.keys[i * 32u + lane];
+          uint32_t score = 0;
+          for (uint32_t a = tx; a; a = parent[a]) score += lane_tab_get(sm, lane, ntab, a);
+          if (score > best_s) {
+            best_s = score;
+            best_t = tx;
+          } else if (score == best_s) {
+            best_t = lca(parent, best_t, tx);
+          }
+        }
+        uint32_t max_taxon = best_t;
+        uint32_t max_score = max_taxon ? lane_tab_get(sm, lane, ntab, max_taxon) : 0u;
+        const uint32_t required = (uint32_t)ceil(__dmul_rn(sp.confidence, (double)total_kmers));
+        while (max_taxon && max_score < required) {
+          uint32_t sum = 0;
+          for (uint32_t i = 0; i < ntab; i++)
+            if (is_a_ancestor_of_b(parent, max_taxon, sm.keys[i * 32u + lane]))
+              sum += sm.cnts[i * 32u + lane];
+          max_score = sum;
+          if (max_score >= required) break;
+          max_taxon = parent[max_taxon];
+        }
+        uint32_t call = max_taxon;
+        if (call && groups < sp.min_hit_groups) call = 0;
+        const uint32_t is_cls = call != 0u;
+        const uint32_t keep = sp.keep_human ? is_cls : !is_cls;
+        if (b.out_call) b.out_call[u] = call ? db.ext_id[call] : 0u;
+        if (b.out_keep) b.out_keep[u] = (uint8_t)keep;
+        if (b.dbg_call) b.dbg_call[u] = call;
+        if (b.dbg_total_kmers) b.dbg_total_kmers[u] = total_kmers;
+        if (b.dbg_hit_groups) b.dbg_hit_groups[u] = (uint32_t)groups;
+        tot_classified += is_cls;
+        tot_kept += keep;
+      }
+    }
+    __syncwarp();
+  }
+  tot_lookups = warp_sum_u32(tot_lookups);
+  tot_classified = warp_sum_u32(tot_classified);
+  tot_kept = warp_sum_u32(tot_kept);
+  if (lane == 0) {
+    if (tot_lookups) atomicAdd(&b.counters->n_lookups, tot_lookups);
+    if (tot_classified) atomicAdd(&b.counters->n_classified, tot_classified);
+    if (tot_kept) atomicAdd(&b.counters->n_kept, tot_kept);
+  }
+}
+
+/* ------------------------------------------------------------------ */
 /* roofline helper: uniformly random aligned 32-byte sector reads       */
 
 __global__ void __launch_bounds__(256)
@@ -605,6 +918,9 @@ cudaError_t nh_kernels_init(void) {
   e = cudaFuncSetAttribute(k_score<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            NH_SMEM_PARENT_MAX * 4 + NH_WARPS_PER_BLOCK * NH_WARP_HASH_SLOTS * 8);
   if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(k_scan_probe_score<5>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           NH_SMEM_PARENT_MAX * 4 + NH_WARPS_PER_BLOCK * (int)sizeof(FusedWarpSmem));
+  if (e != cudaSuccess) return e;
   g_big_smem_ok = 1;
   return cudaSuccess;
 }
@@ -613,9 +929,28 @@ int nh_launch_plan(const NhDbParams &db, const NhBatchPtrs &b, cudaStream_t st) 
   const uint32_t nb = (b.n_seqs + PLAN_THREADS - 1) / PLAN_THREADS;
   k_plan_count<<<nb, PLAN_THREADS, 0, st>>>(b.offsets, b.n_seqs, db.k, db.tile_pos, b.block_sums);
   k_plan_scan<<<1, PLAN_THREADS, 0, st>>>(b.block_sums, nb, b.counters);
-  k_plan_fill<<<nb, PLAN_THREADS, 0, st>>>(b.offsets, b.n_seqs, db.k, db.tile_pos, b.block_sums,
-                                           b.tile_base, b.tiles, b.counters);
+  k_plan_fill<<<nb, PLAN_THREADS, 0, st>>>(b.offsets, b.n_seqs, db.k, db.tile_pos, b.paired,
+                                           b.deferred_units != nullptr, b.block_sums, b.tile_base,
+                                           b.tiles, b.deferred_units, b.counters);
   return 3;
+}
+
+bool nh_fused_supported(const NhDbParams &db) { return db.w == 5 && db.tile_pos <= 255; }
+
+static size_t fused_smem_bytes(const NhDbParams &db) {
+  const uint32_t parent_words = db.node_count <= NH_SMEM_PARENT_MAX ? db.node_count : 0u;
+  return (size_t)((parent_words + 3u) & ~3u) * 4 + NH_WARPS_PER_BLOCK * sizeof(FusedWarpSmem);
+}
+
+int nh_launch_fused(const NhDbParams &db, const NhBatchPtrs &b, const NhScoreParams &sp,
+                    uint32_t tiles_upper, int sm_count, cudaStream_t st) {
+  uint32_t groups = (tiles_upper + 31u) / 32u;
+  uint32_t blocks = (groups + NH_WARPS_PER_BLOCK - 1) / NH_WARPS_PER_BLOCK;
+  uint32_t max_grid = (uint32_t)sm_count * 4u;
+  uint32_t grid = blocks < max_grid ? blocks : max_grid;
+  if (grid == 0) grid = 1;
+  k_scan_probe_score<5><<<grid, NH_BLOCK_THREADS, fused_smem_bytes(db), st>>>(db, b, sp);
+  return 1;
 }
 
 int nh_launch_minimizers(const NhDbParams &db, const NhBatchPtrs &b, uint32_t tiles_upper,

@@ -39,10 +39,20 @@ struct NhDbParams {
   uint32_t node_count;
 };
 
-struct NhTile {
+struct __align__(16) NhTile {
   uint32_t seq;       /* sequence index in the batch */
   uint32_t pos_begin; /* first k-mer position of the tile */
+  uint32_t slot;      /* first lookup slot of the tile = k-mer positions before it in the batch */
+  uint32_t role;      /* who scores the tile's unit inside k_scan_probe_score, NH_ROLE_* */
 };
+
+/* roles of a tile in the fused kernel: a unit is scored in-warp when each of
+ * its mates is at most one tile and both tiles sit in the same group of 32 */
+#define NH_ROLE_DEFERRED 0u /* unit goes to k_score (multi-tile or split across groups) */
+#define NH_ROLE_LEADER 1u   /* scores its unit from its own tile */
+#define NH_ROLE_LEADER2 2u  /* scores its unit from its own tile and tile + 1 */
+#define NH_ROLE_PARTNER 3u  /* second mate; the lane before scores the unit */
+#define NH_LANE_TAXA 8      /* per-lane taxon->count slots in the fused kernel */
 
 struct NhTileOut {
   uint32_t lk_off; /* first lookup of the tile in the lookup arrays */
@@ -57,7 +67,8 @@ struct NhCounters {
   uint32_t n_kept;
   uint32_t n_overflow;   /* units sent to the big-table scoring pass */
   uint32_t error;        /* nonzero: a unit exceeded even the big table */
-  uint32_t pad[2];
+  uint32_t n_deferred;   /* units k_score handles (not scored inside the fused kernel) */
+  uint32_t pad[1];
 };
 
 struct NhBatchPtrs {
@@ -68,7 +79,7 @@ struct NhBatchPtrs {
   int32_t paired;
   /* plan */
   uint32_t *tile_base;      /* n_seqs + 1: first tile of each sequence */
-  uint32_t *block_sums;
+  uint64_t *block_sums;
   NhTile *tiles;
   NhTileOut *tile_out;
   /* lookups */
@@ -82,6 +93,7 @@ struct NhBatchPtrs {
   uint32_t *dbg_total_kmers;
   uint32_t *dbg_hit_groups;
   uint32_t *overflow_units;
+  uint32_t *deferred_units; /* null: k_score walks every unit (legacy path) */
   NhCounters *counters;
   /* per-position debug output of the minimizer kernel (may be null) */
   const uint64_t *dbg_pos_offsets;
@@ -97,6 +109,10 @@ struct NhScoreParams {
 
 /* launchers (nh_kernels.cu); each returns the number of kernels launched */
 int nh_launch_plan(const NhDbParams &db, const NhBatchPtrs &b, cudaStream_t st);
+/* fused path: lane-serial minimizer scan -> probe -> in-warp scoring of short units */
+bool nh_fused_supported(const NhDbParams &db);
+int nh_launch_fused(const NhDbParams &db, const NhBatchPtrs &b, const NhScoreParams &sp,
+                    uint32_t tiles_upper, int sm_count, cudaStream_t st);
 int nh_launch_minimizers(const NhDbParams &db, const NhBatchPtrs &b, uint32_t tiles_upper,
                          int sm_count, cudaStream_t st);
 int nh_launch_probe(const NhDbParams &db, const uint64_t *keys, uint32_t *taxa,
