@@ -434,6 +434,10 @@ extern "C" int nh_session_create(nh_db *db, const nh_params_t *params, nh_sessio
     /* NH_LEGACY_KERNELS=1 forces the warp-per-tile kernels (A/B runs, generic window widths) */
     const char *legacy = getenv("NH_LEGACY_KERNELS");
     s->use_fused = nh_fused_supported(db->params) && !(legacy && legacy[0] == '1');
+    /* NH_TEST_LANE_TAXA=n shrinks the in-warp taxon table so tests reach the overflow pass */
+    const char *lt = getenv("NH_TEST_LANE_TAXA");
+    int v = lt ? atoi(lt) : NH_LANE_TAXA;
+    s->lane_taxa = v < 1 ? 1 : (v > NH_LANE_TAXA ? NH_LANE_TAXA : v);
   }
   const NhDbParams &P = db->params;
   /* every sequence has at most ceil(positions / tile_pos) tiles */
@@ -557,6 +561,7 @@ static int enqueue_batch(nh_session *s, const uint8_t *d_bases, const uint64_t *
   SP.confidence = s->params.confidence;
   SP.min_hit_groups = s->params.minimum_hit_groups;
   SP.keep_human = s->params.keep_human;
+  SP.lane_taxa = s->lane_taxa;
   const int sm = s->db->sm_count;
   uint64_t tiles_upper = n_seqs + total_bases / (uint64_t)P.tile_pos + 1;
   uint64_t lookups_upper = total_bases;

@@ -54,6 +54,7 @@ struct nh_session {
   uint32_t *d_overflow = nullptr;
   uint32_t *d_deferred = nullptr;
   bool use_fused = false, last_fused = false;
+  int lane_taxa = NH_LANE_TAXA;
   NhCounters *d_counters = nullptr;
   NhCounters *h_counters = nullptr; /* pinned */
   cudaStream_t stream = nullptr;

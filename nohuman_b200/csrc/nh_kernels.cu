@@ -461,7 +461,7 @@ __device__ __forceinline__ uint32_t lca(const uint32_t *parent, uint32_t a, uint
 __device__ bool score_unit(const NhDbParams &db, const NhBatchPtrs &b, const NhScoreParams &sp,
                            const uint32_t *parent, uint32_t *keys, uint32_t *cnts,
                            uint32_t cap_mask, uint32_t u, uint32_t lane, uint32_t *classified,
-                           uint32_t *kept) {
+                           uint32_t *kept, bool reprobe = false) {
   for (uint32_t s = lane; s <= cap_mask; s += 32u) {
     keys[s] = 0;
     cnts[s] = 0;
@@ -481,7 +481,7 @@ __device__ bool score_unit(const NhDbParams &db, const NhBatchPtrs &b, const NhS
     for (uint32_t tile = t0; tile < t1; tile++) {
       const NhTileOut to = b.tile_out[tile];
       for (uint32_t j = lane; j < to.lk_cnt; j += 32u) {
-        const uint32_t tx = b.lk_taxon[to.lk_off + j];
+        const uint32_t tx = reprobe ? cht_get(db, b.lk_min[to.lk_off + j]) : b.lk_taxon[to.lk_off + j];
         if (tx) {
           groups++;
           ok &= hc_add(keys, cnts, cap_mask, tx, b.lk_cnt[to.lk_off + j]);
@@ -491,7 +491,7 @@ __device__ bool score_unit(const NhDbParams &db, const NhBatchPtrs &b, const NhS
         /* a tile starts with a fresh lookup even when its first minimizer equals
          * the last one of the previous tile: upstream counts that as one group */
         if (lane == 0 && tile > t0 && b.lk_min[to.lk_off] == prev_last &&
-            b.lk_taxon[to.lk_off] != 0u)
+            (reprobe ? cht_get(db, b.lk_min[to.lk_off]) : b.lk_taxon[to.lk_off]) != 0u)
           groups--;
         prev_last = b.lk_min[to.lk_off + to.lk_cnt - 1u];
       }
@@ -599,9 +599,10 @@ k_score_big(const NhDbParams db, const NhBatchPtrs b, const NhScoreParams sp) {
   const uint32_t n = b.counters->n_overflow;
   uint32_t classified = 0, kept = 0;
   for (uint32_t i = blockIdx.x; i < n; i += gridDim.x) {
-    const uint32_t u = b.overflow_units[i];
+    const uint32_t raw = b.overflow_units[i];
+    const uint32_t u = raw & ~NH_OVERFLOW_REPROBE;
     if (!score_unit(db, b, sp, db.parent, keys, cnts, NH_BIG_HASH_SLOTS - 1u, u, lane,
-                    &classified, &kept)) {
+                    &classified, &kept, (raw & NH_OVERFLOW_REPROBE) != 0u)) {
       if (lane == 0) atomicExch(&b.counters->error, 1u);
     }
   }
@@ -622,20 +623,33 @@ k_score_big(const NhDbParams db, const NhBatchPtrs b, const NhScoreParams sp) {
  *            stay in L2 for phase B).  ~1/3 of the instructions of the
  *            warp-per-tile kernel, because nothing is recomputed per l-mer.
  *   phase B  the group's lookups are flattened over the 32 lanes and probed
- *            (same cht_get as k_probe), so every lane has a DRAM request in
- *            flight while other warps of the SM are in phase A.
- *   phase C  lanes that lead a short unit (roles from k_plan_fill) fold the
- *            taxa of their tile (+ the mate's tile) into a per-lane table and
- *            run ResolveTree serially; other units are left to k_score.
+ *            in rounds.  A lane whose probe chain runs into the next sector
+ *            does not loop on its own: it pushes the continuation onto a
+ *            32-entry queue in shared memory and the next round hands the
+ *            queue and fresh lookups out over all 32 lanes again, so every
+ *            round has 32 independent DRAM requests in flight.  Results are
+ *            folded straight into the owning unit's taxon table (shared-memory
+ *            atomics); only tiles of deferred units write lk_taxon.
+ *   phase C  lanes that lead a short unit (roles from k_plan_fill) run
+ *            ResolveTree serially on their table; other units go to k_score.
  * Only the window width W is a template parameter (kraken2's default
  * k=35,l=31 gives W=5); other databases take the warp-per-tile kernels.
  */
 
-struct FusedWarpSmem {
+#define NH_META_DEFERRED 0x80u
+
+struct __align__(16) FusedWarpSmem {
+  uint64_t q_sec[32];                    /* continuation queue: next sector to read */
+  uint32_t q_ckey[32];
+  uint32_t q_slot[32];
+  uint32_t q_aux[32];                    /* owner tile | sectors visited << 5 */
   uint32_t prefix[33];                   /* exclusive scan of lookups per tile */
   uint32_t slot[32];                     /* first lookup slot of each tile */
-  uint32_t keys[NH_LANE_TAXA * 32];      /* [slot][lane] */
+  uint32_t keys[NH_LANE_TAXA * 32];      /* taxon tables, [slot][owner lane] */
   uint32_t cnts[NH_LANE_TAXA * 32];
+  uint32_t groups[32];                   /* minimizer_hit_groups per owner lane */
+  uint8_t meta[32];                      /* per tile: owner lane | NH_META_DEFERRED */
+  uint32_t overflow;                     /* bit per owner lane: table overflowed */
 };
 
 __device__ __forceinline__ uint32_t lane_tab_get(const FusedWarpSmem &sm, uint32_t lane,
@@ -648,7 +662,7 @@ __device__ __forceinline__ uint32_t lane_tab_get(const FusedWarpSmem &sm, uint32
 template <int W>
 __global__ void __launch_bounds__(NH_BLOCK_THREADS)
 k_scan_probe_score(const NhDbParams db, const NhBatchPtrs b, const NhScoreParams sp) {
-  extern __shared__ uint32_t s_dyn[];
+  extern __shared__ __align__(16) uint32_t s_dyn[];
   uint32_t *s_parent = s_dyn;
   const bool smem_parent = db.node_count <= NH_SMEM_PARENT_MAX;
   const uint32_t parent_words = smem_parent ? db.node_count : 0u;
@@ -659,11 +673,15 @@ k_scan_probe_score(const NhDbParams db, const NhBatchPtrs b, const NhScoreParams
   }
   const uint32_t *parent = smem_parent ? s_parent : db.parent;
   const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+  const uint32_t lane_lt = (1u << lane) - 1u;
   FusedWarpSmem &sm = s_warps[warp];
   const uint32_t n_tiles = b.counters->n_tiles;
   const int k = db.k, l = db.l;
   const uint64_t lmask = (1ULL << (2 * l)) - 1ULL;
   const uint32_t rc_shift = 2u * (uint32_t)(l - 1);
+  const uint64_t n_sectors = (db.capacity + 7ULL) >> 3;
+  /* probe-chain guard for a table without any empty cell (never a real database) */
+  const uint32_t max_visits = n_sectors + 1ULL < 0x7FFFFFFULL ? (uint32_t)(n_sectors + 1ULL) : 0x7FFFFFFu;
   uint32_t tot_lookups = 0, tot_classified = 0, tot_kept = 0;
 
   for (uint32_t group = blockIdx.x * NH_WARPS_PER_BLOCK + warp; group * 32u < n_tiles;
@@ -673,6 +691,15 @@ k_scan_probe_score(const NhDbParams db, const NhBatchPtrs b, const NhScoreParams
     NhTile t;
     t.seq = 0; t.pos_begin = 0; t.slot = 0; t.role = NH_ROLE_DEFERRED;
     if (have) t = b.tiles[tile];
+#pragma unroll
+    for (int i = 0; i < NH_LANE_TAXA; i++) {
+      sm.keys[i * 32 + lane] = 0;
+      sm.cnts[i * 32 + lane] = 0;
+    }
+    sm.groups[lane] = 0;
+    if (lane == 0) sm.overflow = 0;
+    sm.meta[lane] = (uint8_t)(t.role == NH_ROLE_DEFERRED ? NH_META_DEFERRED
+                              : (t.role == NH_ROLE_PARTNER ? lane - 1u : lane));
 
     /* ---------------- phase A: lane-serial minimizer scan ---------------- */
     uint32_t n_runs = 0;
@@ -687,10 +714,10 @@ k_scan_probe_score(const NhDbParams db, const NhBatchPtrs b, const NhScoreParams
         nb = npos + (uint32_t)k - 1u;
       }
       const uint8_t *g = b.bases + so + t.pos_begin;
-      const uint32_t mis = (uint32_t)((uintptr_t)g & 15u);
-      const uint4 *q = reinterpret_cast<const uint4 *>(g - mis);
-      const uint32_t my_chunks = have ? (mis + nb + 15u) >> 4 : 0u;
-      const uint32_t max_chunks = __reduce_max_sync(FULL_MASK, my_chunks);
+      const uint32_t mis = (uint32_t)((uintptr_t)g & 3u);
+      const uint32_t *q = reinterpret_cast<const uint32_t *>(g - mis);
+      const uint32_t my_words = have ? (mis + nb + 3u) >> 2 : 0u;
+      const uint32_t max_words = __reduce_max_sync(FULL_MASK, my_words);
 
       uint64_t fwd = 0, rc = 0;
       uint64_t ring[W > 1 ? W - 1 : 1];
@@ -703,60 +730,56 @@ k_scan_probe_score(const NhDbParams db, const NhBatchPtrs b, const NhScoreParams
       uint8_t *out_cnt = b.lk_cnt + t.slot;
       const bool dbg = b.dbg_pos_min != nullptr;
       const uint64_t dbg_base = dbg && have ? b.dbg_pos_offsets[t.seq] + t.pos_begin : 0;
+      const uint32_t first_pos = mis + (uint32_t)(k - 1); /* word-stream index of the first k-mer end */
+      const uint32_t end_idx = mis + nb;
 
-      for (uint32_t ch = 0; ch < max_chunks; ch++) {
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (ch < my_chunks) v = __ldg(q + ch);
-        uint32_t a0, a1, a2, a3;
-        const uint32_t p0 = nh_pack4(v.x, &a0), p1 = nh_pack4(v.y, &a1);
-        const uint32_t p2 = nh_pack4(v.z, &a2), p3 = nh_pack4(v.w, &a3);
-        const uint32_t codes = (p0 << 24) | (p1 << 16) | (p2 << 8) | p3; /* first base in the MSBs */
-        const uint32_t ambs = a0 | (a1 << 4) | (a2 << 8) | (a3 << 12);   /* bit i = base i */
+      /* W - 1 bases per inner iteration: the ring shift is then pure register renaming */
+      uint32_t wv = 0, codes = 0, ambs = 0;
+      for (uint32_t base_i = 0; base_i < max_words * 4u; base_i += (uint32_t)(W > 1 ? W - 1 : 1)) {
 #pragma unroll
-        for (int j = 0; j < 16; j++) {
-          const uint32_t idx = ch * 16u + (uint32_t)j - mis; /* base index in the tile (wraps when before it) */
-          if (idx < nb) {
-            const uint32_t c = (codes >> (30 - 2 * j)) & 3u;
-            const bool amb = (ambs >> j) & 1u;
-            fwd = ((fwd << 2) | c) & lmask;
-            rc = (rc >> 2) | ((uint64_t)(3u - c) << rc_shift);
-            c_run = amb ? 0u : c_run + 1u;
-            uint64_t cand = NH_NONE64;
-            if (c_run >= (uint32_t)l) {
-              const uint64_t rcv = db.revcom_version == 0
-                                       ? (((rc << (64 - 2 * l)) | ((1ULL << (64 - 2 * l)) - 1ULL)) & lmask)
-                                       : rc;
-              cand = ((fwd < rcv ? fwd : rcv) & db.seed_mask) ^ db.toggle;
-            }
-            uint64_t m = cand;
-#pragma unroll
-            for (int i = 0; i < W - 1; i++) m = min_u64(m, ring[i]);
-#pragma unroll
-            for (int i = W - 2; i > 0; i--) ring[i] = ring[i - 1];
-            if (W > 1) ring[0] = cand;
-            if (idx >= (uint32_t)(k - 1)) {
-              const bool nonamb = c_run >= (uint32_t)db.amb_span;
-              const uint64_t mz = m ^ db.toggle;
-              if (dbg) {
-                const uint64_t o = dbg_base + (idx - (uint32_t)(k - 1));
-                b.dbg_pos_min[o] = mz;
-                b.dbg_pos_ambig[o] = nonamb ? 0 : 1;
-              }
-              if (nonamb) {
-                if (mz != last) {
-                  if (cnt) {
-                    out_min[n_runs] = last;
-                    out_cnt[n_runs] = (uint8_t)cnt;
-                    n_runs++;
-                  }
-                  last = mz;
-                  cnt = 1;
-                } else {
-                  cnt++;
-                }
-              }
-            }
+        for (int j = 0; j < (W > 1 ? W - 1 : 1); j++) {
+          const uint32_t i = base_i + (uint32_t)j; /* index in the word-aligned stream */
+          if ((i & 3u) == 0u) {
+            wv = (i >> 2) < my_words ? __ldg(q + (i >> 2)) : 0u;
+            codes = nh_pack4(wv, &ambs); /* first base in bits 7..6 */
           }
+          const uint32_t sh = 6u - 2u * (i & 3u);
+          const uint32_t c = (codes >> sh) & 3u;
+          const bool inside = i >= mis && i < end_idx;
+          /* bytes outside the tile count as ambiguous: they reset the l-mer and never reach a position */
+          const bool amb = ((ambs >> (i & 3u)) & 1u) || !inside;
+          fwd = ((fwd << 2) | c) & lmask;
+          rc = (rc >> 2) | ((uint64_t)(3u - c) << rc_shift);
+          c_run = amb ? 0u : c_run + 1u;
+          uint64_t cand = NH_NONE64;
+          if (c_run >= (uint32_t)l) {
+            const uint64_t rcv = db.revcom_version == 0
+                                     ? (((rc << (64 - 2 * l)) | ((1ULL << (64 - 2 * l)) - 1ULL)) & lmask)
+                                     : rc;
+            cand = ((fwd < rcv ? fwd : rcv) & db.seed_mask) ^ db.toggle;
+          }
+          uint64_t m = cand;
+#pragma unroll
+          for (int r = 0; r < W - 1; r++) m = min_u64(m, ring[r]);
+#pragma unroll
+          for (int r = W - 2; r > 0; r--) ring[r] = ring[r - 1];
+          if (W > 1) ring[0] = cand;
+          const bool at_pos = inside && i >= first_pos;
+          const bool nonamb = at_pos && c_run >= (uint32_t)db.amb_span;
+          const uint64_t mz = m ^ db.toggle;
+          if (dbg && at_pos) {
+            const uint64_t o = dbg_base + (i - first_pos);
+            b.dbg_pos_min[o] = mz;
+            b.dbg_pos_ambig[o] = nonamb ? 0 : 1;
+          }
+          const bool newrun = nonamb && mz != last;
+          if (newrun && cnt) {
+            out_min[n_runs] = last;
+            out_cnt[n_runs] = (uint8_t)cnt;
+            n_runs++;
+          }
+          cnt = newrun ? 1u : cnt + (nonamb ? 1u : 0u);
+          last = newrun ? mz : last;
         }
       }
       if (cnt) {
@@ -785,53 +808,110 @@ k_scan_probe_score(const NhDbParams db, const NhBatchPtrs b, const NhScoreParams
     if (lane == 31) sm.prefix[32] = total;
     __syncwarp(); /* also orders the lookup slots written above before the reads below */
     tot_lookups += n_runs;
-    for (uint32_t e = lane; e < total; e += 32u) {
-      /* owner tile: largest o with prefix[o] <= e */
-      uint32_t o = 0;
-#pragma unroll
-      for (int step = 16; step >= 1; step >>= 1)
-        if (sm.prefix[o + step] <= e) o += (uint32_t)step;
-      const uint32_t oslot = sm.slot[o] + (e - sm.prefix[o]);
-      const uint64_t key = __ldcg(b.lk_min + oslot);
-      b.lk_taxon[oslot] = cht_get(db, key);
-    }
-    __syncwarp();
 
-    /* ---------------- phase C: score short units in the warp ---------------- */
-    const uint32_t n_next = __shfl_down_sync(FULL_MASK, n_runs, 1);
-    const uint32_t slot_next = __shfl_down_sync(FULL_MASK, t.slot, 1);
-    if (have && (t.role == NH_ROLE_LEADER || t.role == NH_ROLE_LEADER2)) {
-      uint32_t ntab = 0;
-      int groups = 0;
-      bool ok = true;
-      const uint32_t parts = t.role == NH_ROLE_LEADER2 ? 2u : 1u;
-      for (uint32_t part = 0; part < parts; part++) {
-        const uint32_t base = part ? slot_next : t.slot;
-        const uint32_t n = part ? n_next : n_runs;
-        for (uint32_t j = 0; j < n; j++) {
-          const uint32_t tx = __ldcg(b.lk_taxon + base + j);
-          if (!tx) continue;
-          groups++;
-          const uint32_t c = (uint32_t)__ldcg(b.lk_cnt + base + j);
-          uint32_t i = 0;
-          for (; i < ntab; i++)
-            if (sm.keys[i * 32u + lane] == tx) break;
-          if (i < ntab) {
-            sm.cnts[i * 32u + lane] += c;
-          } else if (ntab < NH_LANE_TAXA) {
-            sm.keys[ntab * 32u + lane] = tx;
-            sm.cnts[ntab * 32u + lane] = c;
-            ntab++;
+    uint32_t qn = 0, e_next = 0;
+    while (qn != 0u || e_next < total) {
+      bool active = false, done = false;
+      uint64_t sec = 0;
+      uint32_t ckey = 0, oslot = 0, aux = 0, start = 0, result = 0;
+      if (lane < qn) {
+        sec = sm.q_sec[lane];
+        ckey = sm.q_ckey[lane];
+        oslot = sm.q_slot[lane];
+        aux = sm.q_aux[lane];
+        active = true;
+      } else {
+        const uint32_t e = e_next + (lane - qn);
+        if (e < total) {
+          uint32_t o = 0; /* owner tile: largest o with prefix[o] <= e */
+#pragma unroll
+          for (int step = 16; step >= 1; step >>= 1)
+            if (sm.prefix[o + step] <= e) o += (uint32_t)step;
+          oslot = sm.slot[o] + (e - sm.prefix[o]);
+          aux = o;
+          const uint64_t h = nh_fmix64(__ldcg(b.lk_min + oslot));
+          active = true;
+          if (db.min_hash && h < db.min_hash) {
+            done = true; /* below minimum_acceptable_hash_value: no lookup, taxon 0 */
           } else {
-            ok = false;
+            ckey = (uint32_t)(h >> (32u + db.value_bits));
+            const uint64_t idx = nh_fastmod(h, db.capacity, db.mod_m, db.mod_sh1, db.mod_sh2);
+            sec = idx >> 3;
+            start = (uint32_t)idx & 7u;
           }
         }
       }
+      e_next += 32u - qn;
+      __syncwarp(); /* queue fully read before it is refilled */
+      if (active && !done) {
+        uint32_t c[8];
+        ld_sector(db.cells + sec * 8ULL, c);
+        const uint64_t rem = db.capacity - sec * 8ULL;
+        const uint32_t limit = rem < 8ULL ? (uint32_t)rem : 8u;
+        const uint32_t range = (0xFFu << start) & ((1u << limit) - 1u);
+        int state = -1;
+#pragma unroll
+        for (int j = 7; j >= 0; j--) {
+          const uint32_t val = c[j] & db.value_mask;
+          const bool term = (val == 0u) || ((c[j] >> db.value_bits) == ckey);
+          if (term && ((range >> j) & 1u)) state = (int)val;
+        }
+        if (state >= 0) {
+          done = true;
+          result = (uint32_t)state;
+        } else {
+          const uint32_t visits = (aux >> 5) + 1u;
+          if (visits >= max_visits) {
+            done = true; /* went round a table without an empty cell */
+          } else {
+            aux = (aux & 31u) | (visits << 5);
+            sec = sec + 1ULL >= n_sectors ? 0ULL : sec + 1ULL;
+          }
+        }
+      }
+      const bool cont = active && !done;
+      const uint32_t cmask = __ballot_sync(FULL_MASK, cont);
+      if (cont) {
+        const uint32_t pos = __popc(cmask & lane_lt);
+        sm.q_sec[pos] = sec;
+        sm.q_ckey[pos] = ckey;
+        sm.q_slot[pos] = oslot;
+        sm.q_aux[pos] = aux;
+      }
+      qn = __popc(cmask);
+      if (active && done) {
+        const uint32_t mt = sm.meta[aux & 31u];
+        if (mt & NH_META_DEFERRED) {
+          b.lk_taxon[oslot] = result;
+        } else if (result) {
+          const uint32_t own = mt;
+          const uint32_t n = (uint32_t)__ldcg(b.lk_cnt + oslot);
+          atomicAdd(&sm.groups[own], 1u);
+          int i = 0;
+          for (; i < sp.lane_taxa; i++) {
+            const uint32_t old = atomicCAS(&sm.keys[i * 32 + own], 0u, result);
+            if (old == 0u || old == result) {
+              atomicAdd(&sm.cnts[i * 32 + own], n);
+              break;
+            }
+          }
+          if (i == sp.lane_taxa) atomicOr(&sm.overflow, 1u << own);
+        }
+      }
+      __syncwarp();
+    }
+
+    /* ---------------- phase C: score short units in the warp ---------------- */
+    if (have && (t.role == NH_ROLE_LEADER || t.role == NH_ROLE_LEADER2)) {
       const uint32_t u = b.paired ? (t.seq >> 1) : t.seq;
-      if (!ok) {
-        /* more distinct taxa than a lane table holds: k_score_big takes the unit */
-        b.overflow_units[atomicAdd(&b.counters->n_overflow, 1u)] = u;
+      if ((sm.overflow >> lane) & 1u) {
+        /* more distinct taxa than a lane table holds: the big-table pass takes the unit.
+         * Its taxa were folded, not stored, so the flag bit tells k_score_big to probe again. */
+        b.overflow_units[atomicAdd(&b.counters->n_overflow, 1u)] = u | NH_OVERFLOW_REPROBE;
       } else {
+        uint32_t ntab = 0;
+        while (ntab < (uint32_t)sp.lane_taxa && sm.keys[ntab * 32u + lane] != 0u) ntab++;
+        const int groups = (int)sm.groups[lane];
         const uint32_t s0 = b.paired ? (t.seq & ~1u) : t.seq;
         uint32_t total_kmers = 0;
         for (uint32_t mm = 0; mm < (b.paired ? 2u : 1u); mm++) {

@@ -53,6 +53,7 @@ struct __align__(16) NhTile {
 #define NH_ROLE_LEADER2 2u  /* scores its unit from its own tile and tile + 1 */
 #define NH_ROLE_PARTNER 3u  /* second mate; the lane before scores the unit */
 #define NH_LANE_TAXA 8      /* per-lane taxon->count slots in the fused kernel */
+#define NH_OVERFLOW_REPROBE 0x80000000u /* overflow_units flag: taxa were not stored, probe again */
 
 struct NhTileOut {
   uint32_t lk_off; /* first lookup of the tile in the lookup arrays */
@@ -105,6 +106,7 @@ struct NhScoreParams {
   double confidence;
   int32_t min_hit_groups;
   int32_t keep_human;
+  int32_t lane_taxa;   /* fused kernel: taxon slots per unit before it overflows (<= NH_LANE_TAXA) */
 };
 
 /* launchers (nh_kernels.cu); each returns the number of kernels launched */

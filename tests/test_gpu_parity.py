@@ -116,3 +116,30 @@ def test_edge_cases(small_db, gpu_db):
         pseqs += [a, b]
     with Session(gpu_db, paired=True, confidence=0.2) as sess:
         _compare_batch(small_db, sess, pseqs, True, 0.2)
+
+
+@pytest.mark.parametrize("mode", ["legacy", "lane_taxa_1", "lane_taxa_2"])
+def test_kernel_path_variants_match_oracle(small_db, gpu_db, mode, monkeypatch):
+    """The warp-per-tile kernels (NH_LEGACY_KERNELS=1) and the fused kernel with a
+    shrunken in-warp taxon table (units overflow into k_score_big, which probes
+    again) give the same answers as the default fused path and the oracle."""
+    from nohuman_b200 import Session
+    if mode == "legacy":
+        monkeypatch.setenv("NH_LEGACY_KERNELS", "1")
+    else:
+        monkeypatch.setenv("NH_TEST_LANE_TAXA", mode[-1])
+    g = dict(small_db.genomes)
+    seqs = synth.illumina_reads(small_db.genomes, 1500, 150, seed=31, paired=True)
+    # chimeric pairs that hit several taxa at once
+    for i in range(100):
+        a = np.concatenate([g[9606][i * 40:i * 40 + 75], g[562][i * 30:i * 30 + 75]])
+        b_ = np.concatenate([g[564][i * 50:i * 50 + 75], g[1423][i * 20:i * 20 + 75]])
+        seqs += [a, b_]
+    seqs += synth.ont_reads(small_db.genomes, 20, seed=5, n50=2000, max_len=8000)[:20]
+    if len(seqs) % 2:
+        seqs.append(seqs[-1][:100])
+    with Session(gpu_db, confidence=0.1, paired=True) as sess:
+        call, keep, st, want = _compare_batch(small_db, sess, seqs, True, 0.1)
+        assert bool(st.fused_kernel) == (mode != "legacy")
+    assert st.n_classified == int((want["call"] != 0).sum())
+    assert len(set(want["call"].tolist())) > 4
