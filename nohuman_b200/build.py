@@ -24,6 +24,8 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC,-O3,-Wall,-pthread",
     "-Xptxas", "-v",
 ]
+# experiment hook: NH_NVCC_EXTRA='-DNH_LD_SECTOR_OP="ld.global.L2::64B.v8.u32"' python -m nohuman_b200.build --force
+NVCC_FLAGS += [f for f in os.environ.get("NH_NVCC_EXTRA", "").split() if f]
 
 
 def _nvcc() -> str:

@@ -362,7 +362,10 @@ k_minimizers(const NhDbParams db, const NhBatchPtrs b) {
 
 __device__ __forceinline__ void ld_sector(const uint32_t *p, uint32_t (&c)[8]) {
   /* one 32-byte sector in one request (256-bit global load, sm_100+) */
-  asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+#ifndef NH_LD_SECTOR_OP
+#define NH_LD_SECTOR_OP "ld.global.nc.L1::no_allocate.v8.u32"
+#endif
+  asm volatile(NH_LD_SECTOR_OP " {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                : "=r"(c[0]), "=r"(c[1]), "=r"(c[2]), "=r"(c[3]), "=r"(c[4]), "=r"(c[5]),
                  "=r"(c[6]), "=r"(c[7])
                : "l"(p));
