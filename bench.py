@@ -247,7 +247,7 @@ def main():
     keep_alive = None
     if use_dist:
         dist.broadcast(meta, 0)
-        nbytes = ((capacity + 7) // 8) * 32
+        nbytes = ((capacity + 31) // 32) * 128
         if rank == 0:
             table = torch.as_tensor(DevPtr(sdb.db.device_cells_ptr(), nbytes), device="cuda")
         else:

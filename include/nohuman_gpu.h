@@ -115,7 +115,9 @@ int nh_db_open(const char *db_dir, int device, nh_db **out);
  * capacity x uint32 cell array (hash.k2d after its 32-byte header); if
  * cells_on_device != 0 it is a device pointer on `device` that the library
  * adopts WITHOUT copying or freeing (used when one rank loads the table and
- * NCCL-broadcasts it to the others). */
+ * NCCL-broadcasts it to the others); it must be 128-byte aligned and readable,
+ * with zero cells, up to the next multiple of 32 cells past `capacity`
+ * (nh_db_device_cells of another nh_db satisfies this). */
 int nh_db_open_memory(const void *opts, size_t opts_len, const void *taxo, size_t taxo_len,
                       const uint64_t hash_header[4], const uint32_t *cells, int cells_on_device,
                       int device, nh_db **out);

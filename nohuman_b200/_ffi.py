@@ -12,7 +12,8 @@ import ctypes as C
 import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libnohuman_gpu.so")
+# NH_LIB_PATH points experiments at another build of the same library (e.g. other nvcc flags)
+LIB_PATH = os.environ.get("NH_LIB_PATH") or os.path.join(_PKG, "libnohuman_gpu.so")
 
 NH_OK = 0
 NH_ERR_INVALID = -1

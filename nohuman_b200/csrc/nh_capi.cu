@@ -225,15 +225,15 @@ extern "C" int nh_db_open_memory(const void *opts, size_t opts_len, const void *
   }
   const uint64_t cap = hash_header[0];
   if (cells_on_device) {
-    if (((uintptr_t)cells & 31u) != 0) {
+    if (((uintptr_t)cells & 127u) != 0) {
       delete db;
-      return nh_set_error(NH_ERR_INVALID, "device cell array must be 32-byte aligned");
+      return nh_set_error(NH_ERR_INVALID, "device cell array must be 128-byte aligned");
     }
     db->d_cells = const_cast<uint32_t *>(cells);
     db->owns_cells = false;
   } else {
-    /* padded to whole sectors so the last sector load stays inside the allocation */
-    const size_t bytes = ((cap + 7) / 8) * 32;
+    /* padded to whole 128-byte lines (zero cells) so a 4-sector group load stays inside the allocation */
+    const size_t bytes = ((cap + 31) / 32) * 128;
     cudaError_t e = cudaMalloc(&db->d_cells, bytes);
     if (e != cudaSuccess) {
       delete db;
@@ -273,7 +273,7 @@ int nh_db_create_empty(const void *opts, size_t opts_len, const void *taxo, size
   }
   uint64_t vb = 1;
   while ((1ULL << vb) < db->info.node_count) vb++;
-  const size_t bytes = ((capacity + 7) / 8) * 32;
+  const size_t bytes = ((capacity + 31) / 32) * 128;
   cudaError_t e = cudaMalloc(&db->d_cells, bytes);
   if (e != cudaSuccess) {
     delete db;
@@ -330,7 +330,7 @@ extern "C" int nh_db_open(const char *db_dir, int device, nh_db **out) {
     return rc;
   }
   const uint64_t cap = hdr[0];
-  const size_t bytes = ((cap + 7) / 8) * 32;
+  const size_t bytes = ((cap + 31) / 32) * 128;
   cudaError_t e = cudaMalloc(&db->d_cells, bytes);
   if (e != cudaSuccess) {
     fclose(f);

@@ -17,6 +17,8 @@
  * and, in the reference itself, the keep/drop polarity of
  * src/main.rs:259-265 (--classified-out vs --unclassified-out).
  */
+#include <stdlib.h>
+
 #include "nh_kernels.cuh"
 
 #define FULL_MASK 0xFFFFFFFFu
@@ -641,11 +643,18 @@ k_score_big(const NhDbParams db, const NhBatchPtrs b, const NhScoreParams sp) {
 
 #define NH_META_DEFERRED 0x80u
 
+#define NH_RING_SKIP 0x80000000u /* below minimum_acceptable_hash_value: no lookup, taxon 0 */
+
 struct __align__(16) FusedWarpSmem {
-  uint64_t q_sec[32];                    /* continuation queue: next sector to read */
+  /* look-ahead ring: the group's lookups hashed 32 at a time (one per lane) */
+  uint32_t r_unit[64];                   /* aligned group of G sectors holding hash % capacity */
+  uint32_t r_ckey[64];
+  uint32_t r_slot[64];
+  uint32_t r_aux[64];                    /* owner tile | start cell in the group << 5 | NH_RING_SKIP */
+  uint32_t q_unit[32];                   /* continuation queue: next group of sectors to read */
   uint32_t q_ckey[32];
   uint32_t q_slot[32];
-  uint32_t q_aux[32];                    /* owner tile | sectors visited << 5 */
+  uint32_t q_aux[32];                    /* owner tile | groups visited << 5 */
   uint32_t prefix[33];                   /* exclusive scan of lookups per tile */
   uint32_t slot[32];                     /* first lookup slot of each tile */
   uint32_t keys[NH_LANE_TAXA * 32];      /* taxon tables, [slot][owner lane] */
@@ -662,9 +671,19 @@ __device__ __forceinline__ uint32_t lane_tab_get(const FusedWarpSmem &sm, uint32
   return 0;
 }
 
-template <int W>
-__global__ void __launch_bounds__(NH_BLOCK_THREADS)
+#ifndef NH_FUSED_MIN_BLOCKS
+#define NH_FUSED_MIN_BLOCKS 4
+#endif
+template <int W, int G>
+__global__ void __launch_bounds__(NH_BLOCK_THREADS, NH_FUSED_MIN_BLOCKS)
 k_scan_probe_score(const NhDbParams db, const NhBatchPtrs b, const NhScoreParams sp) {
+  /* G lanes read the G adjacent sectors of one aligned 32*G-byte group with ONE warp
+   * instruction: the memory system charges one request per instruction and 128-byte line
+   * (profiles/r01_random_access_microbench.txt), so a probe chain that stays inside the
+   * group costs nothing extra. */
+  static_assert(G == 1 || G == 2 || G == 4, "a group is 32, 64 or 128 bytes");
+  constexpr uint32_t NI = 32u / G;          /* lookups per round */
+  constexpr uint32_t GCELLS = 8u * G;       /* cells per group */
   extern __shared__ __align__(16) uint32_t s_dyn[];
   uint32_t *s_parent = s_dyn;
   const bool smem_parent = db.node_count <= NH_SMEM_PARENT_MAX;
@@ -682,9 +701,9 @@ k_scan_probe_score(const NhDbParams db, const NhBatchPtrs b, const NhScoreParams
   const int k = db.k, l = db.l;
   const uint64_t lmask = (1ULL << (2 * l)) - 1ULL;
   const uint32_t rc_shift = 2u * (uint32_t)(l - 1);
-  const uint64_t n_sectors = (db.capacity + 7ULL) >> 3;
+  const uint64_t n_units = (db.capacity + GCELLS - 1ULL) / GCELLS;
   /* probe-chain guard for a table without any empty cell (never a real database) */
-  const uint32_t max_visits = n_sectors + 1ULL < 0x7FFFFFFULL ? (uint32_t)(n_sectors + 1ULL) : 0x7FFFFFFu;
+  const uint32_t max_visits = n_units + 1ULL < 0x7FFFFFFULL ? (uint32_t)(n_units + 1ULL) : 0x7FFFFFFu;
   uint32_t tot_lookups = 0, tot_classified = 0, tot_kept = 0;
 
   for (uint32_t group = blockIdx.x * NH_WARPS_PER_BLOCK + warp; group * 32u < n_tiles;
@@ -737,14 +756,17 @@ k_scan_probe_score(const NhDbParams db, const NhBatchPtrs b, const NhScoreParams
       const uint32_t end_idx = mis + nb;
 
       /* W - 1 bases per inner iteration: the ring shift is then pure register renaming */
-      uint32_t wv = 0, codes = 0, ambs = 0;
-      for (uint32_t base_i = 0; base_i < max_words * 4u; base_i += (uint32_t)(W > 1 ? W - 1 : 1)) {
+      static_assert(W == 5, "the inner loop consumes one 4-byte word per ring rotation");
+      uint32_t codes = 0, ambs = 0;
+      uint32_t w_next = my_words ? __ldg(q) : 0u; /* loaded one word ahead of its use */
+      for (uint32_t base_i = 0; base_i < max_words * 4u; base_i += 4u) {
 #pragma unroll
-        for (int j = 0; j < (W > 1 ? W - 1 : 1); j++) {
+        for (int j = 0; j < 4; j++) {
           const uint32_t i = base_i + (uint32_t)j; /* index in the word-aligned stream */
-          if ((i & 3u) == 0u) {
-            wv = (i >> 2) < my_words ? __ldg(q + (i >> 2)) : 0u;
-            codes = nh_pack4(wv, &ambs); /* first base in bits 7..6 */
+          if (j == 0) {
+            codes = nh_pack4(w_next, &ambs); /* first base in bits 7..6 */
+            const uint32_t wi = (base_i >> 2) + 1u;
+            w_next = wi < my_words ? __ldg(q + wi) : 0u;
           }
           const uint32_t sh = 6u - 2u * (i & 3u);
           const uint32_t c = (codes >> sh) & 3u;
@@ -812,77 +834,109 @@ k_scan_probe_score(const NhDbParams db, const NhBatchPtrs b, const NhScoreParams
     __syncwarp(); /* also orders the lookup slots written above before the reads below */
     tot_lookups += n_runs;
 
-    uint32_t qn = 0, e_next = 0;
+    uint32_t qn = 0, e_next = 0, e_ready = 0;
+    /* hash the next (up to) 32 lookups, one per lane, into the ring */
+    auto prepare = [&]() {
+      uint32_t n = total - e_ready;
+      n = n < 32u ? n : 32u;
+      if (lane < n) {
+        const uint32_t e = e_ready + lane;
+        uint32_t o = 0; /* owner tile: largest o with prefix[o] <= e */
+#pragma unroll
+        for (int step = 16; step >= 1; step >>= 1)
+          if (sm.prefix[o + step] <= e) o += (uint32_t)step;
+        const uint32_t oslot = sm.slot[o] + (e - sm.prefix[o]);
+        const uint64_t h = nh_fmix64(__ldcg(b.lk_min + oslot));
+        uint32_t aux = o | NH_RING_SKIP;
+        if (!(db.min_hash && h < db.min_hash)) {
+          const uint64_t idx = nh_fastmod(h, db.capacity, db.mod_m, db.mod_sh1, db.mod_sh2);
+          sm.r_unit[e & 63u] = (uint32_t)(idx / GCELLS);
+          sm.r_ckey[e & 63u] = (uint32_t)(h >> (32u + db.value_bits));
+          aux = o | ((uint32_t)(idx % GCELLS) << 5);
+        }
+        sm.r_slot[e & 63u] = oslot;
+        sm.r_aux[e & 63u] = aux;
+      }
+      e_ready += n;
+    };
+    prepare();
+    __syncwarp();
+    const uint32_t it = lane / G, sub = lane % G;
     while (qn != 0u || e_next < total) {
-      bool active = false, done = false;
-      uint64_t sec = 0;
-      uint32_t ckey = 0, oslot = 0, aux = 0, start = 0, result = 0;
-      if (lane < qn) {
-        sec = sm.q_sec[lane];
-        ckey = sm.q_ckey[lane];
-        oslot = sm.q_slot[lane];
-        aux = sm.q_aux[lane];
+      bool active = false, skip = false;
+      uint32_t unit = 0, ckey = 0, oslot = 0, aux = 0, start = 0;
+      if (it < qn) {
+        unit = sm.q_unit[it];
+        ckey = sm.q_ckey[it];
+        oslot = sm.q_slot[it];
+        aux = sm.q_aux[it];
         active = true;
       } else {
-        const uint32_t e = e_next + (lane - qn);
+        const uint32_t e = e_next + (it - qn);
         if (e < total) {
-          uint32_t o = 0; /* owner tile: largest o with prefix[o] <= e */
-#pragma unroll
-          for (int step = 16; step >= 1; step >>= 1)
-            if (sm.prefix[o + step] <= e) o += (uint32_t)step;
-          oslot = sm.slot[o] + (e - sm.prefix[o]);
-          aux = o;
-          const uint64_t h = nh_fmix64(__ldcg(b.lk_min + oslot));
           active = true;
-          if (db.min_hash && h < db.min_hash) {
-            done = true; /* below minimum_acceptable_hash_value: no lookup, taxon 0 */
+          oslot = sm.r_slot[e & 63u];
+          const uint32_t ra = sm.r_aux[e & 63u];
+          aux = ra & 31u;
+          if (ra & NH_RING_SKIP) {
+            skip = true;
           } else {
-            ckey = (uint32_t)(h >> (32u + db.value_bits));
-            const uint64_t idx = nh_fastmod(h, db.capacity, db.mod_m, db.mod_sh1, db.mod_sh2);
-            sec = idx >> 3;
-            start = (uint32_t)idx & 7u;
+            unit = sm.r_unit[e & 63u];
+            ckey = sm.r_ckey[e & 63u];
+            start = (ra >> 5) & 31u;
           }
         }
       }
-      e_next += 32u - qn;
-      __syncwarp(); /* queue fully read before it is refilled */
-      if (active && !done) {
-        uint32_t c[8];
-        ld_sector(db.cells + sec * 8ULL, c);
-        const uint64_t rem = db.capacity - sec * 8ULL;
-        const uint32_t limit = rem < 8ULL ? (uint32_t)rem : 8u;
-        const uint32_t range = (0xFFu << start) & ((1u << limit) - 1u);
-        int state = -1;
+      e_next += NI - qn;
+      if (e_next > total) e_next = total;
+      uint32_t c[8];
+      const bool probing = active && !skip;
+      const uint64_t cell0 = ((uint64_t)unit * G + sub) * 8ULL; /* first cell of this lane's sector */
+      if (probing) ld_sector(db.cells + cell0, c);
+      __syncwarp(); /* queue and ring fully read before they are refilled */
+      if (e_ready < total && e_ready - e_next <= 32u) prepare(); /* its key reads overlap the sector reads */
+      int state = -1;
+      if (probing) {
+        /* cells of this sector the chain may stop at: from `start` on, inside the table */
+        const int lo = (int)start - (int)(sub * 8u);
+        uint32_t range = lo <= 0 ? 0xFFu : (lo >= 8 ? 0u : (0xFFu << lo) & 0xFFu);
+        if (cell0 + 8ULL > db.capacity)
+          range &= cell0 >= db.capacity ? 0u : (1u << (uint32_t)(db.capacity - cell0)) - 1u;
 #pragma unroll
         for (int j = 7; j >= 0; j--) {
           const uint32_t val = c[j] & db.value_mask;
           const bool term = (val == 0u) || ((c[j] >> db.value_bits) == ckey);
           if (term && ((range >> j) & 1u)) state = (int)val;
         }
-        if (state >= 0) {
-          done = true;
-          result = (uint32_t)state;
+      }
+      /* the first lane of the G that found a terminal cell has the answer */
+      const uint32_t fmask = __ballot_sync(FULL_MASK, state >= 0);
+      const uint32_t gbase = lane & ~(uint32_t)(G - 1);
+      const uint32_t gbits = (fmask >> gbase) & ((1u << G) - 1u);
+      const uint32_t result_any = (uint32_t)__shfl_sync(FULL_MASK, state, gbase + (gbits ? (uint32_t)__ffs(gbits) - 1u : 0u));
+      bool done = skip || gbits != 0u;
+      uint32_t result = gbits ? result_any : 0u;
+      if (active && !done) {
+        const uint32_t visits = (aux >> 5) + 1u;
+        if (visits >= max_visits) {
+          done = true; /* went round a table without an empty cell */
         } else {
-          const uint32_t visits = (aux >> 5) + 1u;
-          if (visits >= max_visits) {
-            done = true; /* went round a table without an empty cell */
-          } else {
-            aux = (aux & 31u) | (visits << 5);
-            sec = sec + 1ULL >= n_sectors ? 0ULL : sec + 1ULL;
-          }
+          aux = (aux & 31u) | (visits << 5);
+          unit = (uint64_t)unit + 1ULL >= n_units ? 0u : unit + 1u;
         }
       }
-      const bool cont = active && !done;
+      const bool leader = active && sub == 0u;
+      const bool cont = leader && !done;
       const uint32_t cmask = __ballot_sync(FULL_MASK, cont);
       if (cont) {
         const uint32_t pos = __popc(cmask & lane_lt);
-        sm.q_sec[pos] = sec;
+        sm.q_unit[pos] = unit;
         sm.q_ckey[pos] = ckey;
         sm.q_slot[pos] = oslot;
         sm.q_aux[pos] = aux;
       }
       qn = __popc(cmask);
-      if (active && done) {
+      if (leader && done) {
         const uint32_t mt = sm.meta[aux & 31u];
         if (mt & NH_META_DEFERRED) {
           b.lk_taxon[oslot] = result;
@@ -1001,8 +1055,12 @@ cudaError_t nh_kernels_init(void) {
   e = cudaFuncSetAttribute(k_score<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            NH_SMEM_PARENT_MAX * 4 + NH_WARPS_PER_BLOCK * NH_WARP_HASH_SLOTS * 8);
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(k_scan_probe_score<5>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           NH_SMEM_PARENT_MAX * 4 + NH_WARPS_PER_BLOCK * (int)sizeof(FusedWarpSmem));
+  const int fused_max = NH_SMEM_PARENT_MAX * 4 + NH_WARPS_PER_BLOCK * (int)sizeof(FusedWarpSmem);
+  e = cudaFuncSetAttribute(k_scan_probe_score<5, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused_max);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(k_scan_probe_score<5, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused_max);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(k_scan_probe_score<5, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused_max);
   if (e != cudaSuccess) return e;
   g_big_smem_ok = 1;
   return cudaSuccess;
@@ -1018,7 +1076,10 @@ int nh_launch_plan(const NhDbParams &db, const NhBatchPtrs &b, cudaStream_t st) 
   return 3;
 }
 
-bool nh_fused_supported(const NhDbParams &db) { return db.w == 5 && db.tile_pos <= 255; }
+bool nh_fused_supported(const NhDbParams &db) {
+  /* window of 5 l-mers, u8 run lengths, u32 group indices (tables below 128 GiB) */
+  return db.w == 5 && db.tile_pos <= 255 && db.capacity < (1ULL << 35);
+}
 
 static size_t fused_smem_bytes(const NhDbParams &db) {
   const uint32_t parent_words = db.node_count <= NH_SMEM_PARENT_MAX ? db.node_count : 0u;
@@ -1029,10 +1090,24 @@ int nh_launch_fused(const NhDbParams &db, const NhBatchPtrs &b, const NhScorePar
                     uint32_t tiles_upper, int sm_count, cudaStream_t st) {
   uint32_t groups = (tiles_upper + 31u) / 32u;
   uint32_t blocks = (groups + NH_WARPS_PER_BLOCK - 1) / NH_WARPS_PER_BLOCK;
-  uint32_t max_grid = (uint32_t)sm_count * 4u;
+  uint32_t max_grid = (uint32_t)sm_count * NH_FUSED_MIN_BLOCKS;
   uint32_t grid = blocks < max_grid ? blocks : max_grid;
   if (grid == 0) grid = 1;
-  k_scan_probe_score<5><<<grid, NH_BLOCK_THREADS, fused_smem_bytes(db), st>>>(db, b, sp);
+  /* NH_PROBE_LANES=1|2|4: lanes (adjacent sectors) per lookup.  2 and 4 cut the requests per
+   * lookup from 1.41 to 1.24 / 1.12 but cost more issue slots than they save (measured:
+   * 3.67 / 3.81 / 5.27 ms per 1 M pairs), so the default is 1. */
+  static int lanes = 0;
+  if (!lanes) {
+    const char *e = getenv("NH_PROBE_LANES");
+    lanes = e ? atoi(e) : 1;
+    if (lanes != 1 && lanes != 2 && lanes != 4) lanes = 1;
+  }
+  if (lanes == 1)
+    k_scan_probe_score<5, 1><<<grid, NH_BLOCK_THREADS, fused_smem_bytes(db), st>>>(db, b, sp);
+  else if (lanes == 2)
+    k_scan_probe_score<5, 2><<<grid, NH_BLOCK_THREADS, fused_smem_bytes(db), st>>>(db, b, sp);
+  else
+    k_scan_probe_score<5, 4><<<grid, NH_BLOCK_THREADS, fused_smem_bytes(db), st>>>(db, b, sp);
   return 1;
 }
 
