@@ -149,6 +149,33 @@ int nh_session_sync(nh_session *s, nh_batch_stats_t *stats);
 /* The CUDA stream (cudaStream_t) the session launches on. */
 void *nh_session_stream(nh_session *s);
 
+/* ---- file API: the exact stand-in for `kraken.run(&kraken_cmd)` ----
+ * (src/main.rs:270).  One call does what the child process did for the argv
+ * nohuman assembles at src/main.rs:210-267: read 1-2 FASTQ/FASTA inputs
+ * (plain, gzip or bzip2, auto-detected like kraken2 does), classify every
+ * read / pair against the session's database, and write the kept records
+ * (--unclassified-out, or --classified-out when params.keep_human) in input
+ * order.  Unlike kraken2 it writes the FINAL, already compressed outputs, so
+ * the temp-file round trip of src/main.rs:248-257,340-368 disappears.
+ * `stats` carries the three counts parse_kraken_stderr (src/lib.rs:61-97)
+ * extracts from kraken2's stderr; paired counts are pairs. */
+typedef struct {
+  const char *in1;            /* first (or only) input file */
+  const char *in2;            /* second mate file, or NULL for single-end */
+  const char *out1;           /* where kept records of in1 go */
+  const char *out2;           /* ... of in2 (paired only) */
+  int32_t out_format;         /* nohuman -F letter: 'u' none, 'g' gzip, 'b' bzip2, 'x' xz, 'z' zstd; 0 = 'u' */
+  int32_t tag_classified;     /* 1: append " kraken:taxid|<id>" to classified-out headers as kraken2 does */
+  const char *kraken_output;  /* --output: per-read lines; NULL or "/dev/null": not produced */
+  const char *kraken_report;  /* --report; NULL: not produced */
+} nh_files_t;
+int nh_run_files(nh_session *s, const nh_files_t *files, nh_run_stats_t *stats);
+/* Host-logic test hook (no GPU): the same reader -> ordered writer -> block
+ * compressor pipeline with the per-unit decisions (keep[], external call[])
+ * supplied by the caller. */
+int nh_debug_rewrite_files(const nh_files_t *files, const uint8_t *keep, const uint32_t *call_ext,
+                           uint64_t n_units, int threads, nh_run_stats_t *stats);
+
 /* Pinned host memory for callers that want true async copies. */
 void *nh_host_alloc(size_t bytes);
 void nh_host_free(void *p);

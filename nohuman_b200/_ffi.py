@@ -71,6 +71,14 @@ class RunStats(C.Structure):
     ]
 
 
+class Files(C.Structure):
+    _fields_ = [
+        ("in1", C.c_char_p), ("in2", C.c_char_p), ("out1", C.c_char_p), ("out2", C.c_char_p),
+        ("out_format", C.c_int32), ("tag_classified", C.c_int32),
+        ("kraken_output", C.c_char_p), ("kraken_report", C.c_char_p),
+    ]
+
+
 # every symbol include/nohuman_gpu.h declares: name -> (restype, argtypes)
 _vp, _u64, _i32 = C.c_void_p, C.c_uint64, C.c_int
 SYMBOLS = {
@@ -88,6 +96,8 @@ SYMBOLS = {
     "nh_classify_batch": (_i32, [_vp, _vp, _vp, _u64, _vp, _vp, C.POINTER(BatchStats)]),
     "nh_classify_batch_device": (_i32, [_vp, _vp, _vp, _u64, _u64, _vp, _vp]),
     "nh_session_sync": (_i32, [_vp, C.POINTER(BatchStats)]),
+    "nh_run_files": (_i32, [_vp, C.POINTER(Files), C.POINTER(RunStats)]),
+    "nh_debug_rewrite_files": (_i32, [C.POINTER(Files), _vp, _vp, _u64, _i32, C.POINTER(RunStats)]),
     "nh_session_stream": (_vp, [_vp]),
     "nh_host_alloc": (_vp, [C.c_size_t]),
     "nh_host_free": (None, [_vp]),

@@ -14,7 +14,7 @@ import ctypes as C
 import numpy as np
 
 from . import _ffi
-from ._ffi import BatchStats, DbInfo, NhError, Params, check, lib
+from ._ffi import BatchStats, DbInfo, Files, NhError, Params, RunStats, check, lib
 
 
 def parse_confidence_score(text: str) -> float:
@@ -26,8 +26,31 @@ def parse_confidence_score(text: str) -> float:
     except ValueError as e:  # same wording as the reference's error
         raise ValueError("Confidence score must be a number") from e
     if not (0.0 <= float(f32) <= 1.0):
-        raise ValueError("Confidence score must be between 0 and 1")
+        raise ValueError("Confidence score must be in the closed interval [0, 1]")
     return float(np.format_float_positional(f32, unique=True, trim="0"))
+
+
+def make_files(in1, out1, in2=None, out2=None, out_format="u", tag_classified=True) -> Files:
+    f = Files()
+    f.in1 = str(in1).encode()
+    f.in2 = str(in2).encode() if in2 is not None else None
+    f.out1 = str(out1).encode()
+    f.out2 = str(out2).encode() if out2 is not None else None
+    f.out_format = ord(out_format)
+    f.tag_classified = int(tag_classified)
+    return f
+
+
+def rewrite_files(keep: np.ndarray, call_ext: np.ndarray, in1, out1, in2=None, out2=None,
+                  out_format="u", tag_classified=True, threads=2) -> RunStats:
+    """Host-logic test hook (no GPU): the file pipeline with decisions supplied by the caller."""
+    keep = np.ascontiguousarray(keep, dtype=np.uint8)
+    call_ext = np.ascontiguousarray(call_ext, dtype=np.uint32)
+    f = make_files(in1, out1, in2, out2, out_format, tag_classified)
+    st = RunStats()
+    check(lib().nh_debug_rewrite_files(C.byref(f), keep.ctypes.data, call_ext.ctypes.data, len(keep),
+                                       threads, C.byref(st)))
+    return st
 
 
 class Database:
@@ -134,6 +157,16 @@ class Session:
     def sync(self) -> BatchStats:
         st = BatchStats()
         check(lib().nh_session_sync(self._h, C.byref(st)))
+        return st
+
+    # -- file API: what `kraken.run(&kraken_cmd)` + compress() do in the reference --
+    def run_files(self, in1: str, out1: str, in2: str | None = None, out2: str | None = None,
+                  out_format: str = "u", tag_classified: bool = True) -> RunStats:
+        """src/main.rs:270 + :340-368 in one call: classify in1[/in2], write the kept
+        records (final, compressed per out_format u/g/b/x/z) to out1[/out2] in input order."""
+        f = make_files(in1, out1, in2, out2, out_format, tag_classified)
+        st = RunStats()
+        check(lib().nh_run_files(self._h, C.byref(f), C.byref(st)))
         return st
 
     @property

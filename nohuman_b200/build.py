@@ -16,7 +16,7 @@ LIB = os.path.join(PKG, "libnohuman_gpu.so")
 CLI = os.path.join(PKG, "bin", "nohuman")
 
 CU_SOURCES = ["nh_kernels.cu", "nh_capi.cu", "nh_synth.cu"]
-CC_SOURCES = ["nh_pipeline.cc"]
+CC_SOURCES = ["nh_pipeline.cc"]  # host pipeline, compiled into the same library
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -52,7 +52,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     hdrs.append(os.path.join(PKG, "..", "include", "nohuman_gpu.h"))
     if force or _stale(LIB, srcs + hdrs + [os.path.abspath(__file__)]):
         cmd = [_nvcc(), *NVCC_FLAGS, "-ccbin", "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++",
-               "-shared", "-o", LIB, *srcs, "-lz", "-lpthread"]
+               "-shared", "-o", LIB, *srcs, "-lz", "-lpthread", "-ldl"]
         if verbose:
             print(" ".join(cmd))
         r = subprocess.run(cmd, capture_output=True, text=True)
@@ -70,6 +70,11 @@ def build(force: bool = False, verbose: bool = False) -> str:
         cmd = ["/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++", "-O2", "-std=c++17", "-Wall",
                "-o", CLI, main_cc, "-L", PKG, "-lnohuman_gpu", "-Wl,-rpath,$ORIGIN/..", "-lpthread"]
         subprocess.check_call(cmd)
+        # the same binary under the name nohuman looks for on $PATH (src/main.rs:170): argv shim
+        shim = os.path.join(os.path.dirname(CLI), "kraken2")
+        if os.path.lexists(shim):
+            os.remove(shim)
+        shutil.copy2(CLI, shim)
     return LIB
 
 

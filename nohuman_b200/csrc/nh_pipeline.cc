@@ -1,0 +1,822 @@
+/*
+ * nh_pipeline.cc — the file API of libnohuman_gpu.so: nh_run_files() is the
+ * in-process stand-in for `kraken.run(&kraken_cmd)` (reference
+ * src/main.rs:270, argv built at src/main.rs:210-267) plus the compression
+ * pass that follows it (src/main.rs:340-368, src/compression.rs:182-268).
+ *
+ *   reader thread per input file   inflate (zlib; bzip2 through a pipe) + FASTQ/FASTA parse
+ *        |  chunks of NH_CHUNK_RECORDS records
+ *   classifier threads (2)         mates interleaved into PINNED bases/offsets,
+ *        |                         nh_classify_batch (H2D, kernels, D2H) on their own session
+ *   writer thread                  batches back in input order, kept records re-serialised
+ *        |                         the way kraken2 prints them, cut into blocks
+ *   compressor pool (-t threads)   every block an independent gzip member / zstd frame
+ *        |                         (what gzp does for the reference), written in order
+ *   final out1 / out2              no temporary FASTQ, no second pass
+ *
+ * What kraken2 does on this path and is restated here (upstream seqreader.cc /
+ * classify.cc): format auto-detected from the first byte ('@'
+ * FASTQ, '>' FASTA); header/sequence/quality lines stripped of trailing
+ * whitespace; FASTA sequences joined to one line; records written as
+ * header\nseq\n+\nquals\n (or header\nseq\n); classified records get
+ * " kraken:taxid|<external id>" appended to the header; paired input is read
+ * in lock step and stops at the shorter file; output order == input order.
+ */
+#include <dlfcn.h>
+#include <fcntl.h>
+#include <spawn.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/stat.h>
+#include <sys/wait.h>
+#include <unistd.h>
+#include <zlib.h>
+
+#include <chrono>
+#include <condition_variable>
+#include <deque>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/nohuman_gpu.h"
+#include "nh_internal.h"
+
+extern char **environ;
+
+namespace {
+
+constexpr size_t NH_CHUNK_RECORDS = 1u << 16; /* records per reader chunk (per file) */
+constexpr size_t NH_OUT_BLOCK = 1u << 20;     /* uncompressed bytes per compression block */
+
+/* ------------------------------------------------------------------ */
+/* small blocking queue                                                */
+
+template <typename T>
+class Channel {
+ public:
+  explicit Channel(size_t cap) : cap_(cap) {}
+  bool push(T &&v) {
+    std::unique_lock<std::mutex> lk(m_);
+    not_full_.wait(lk, [&] { return q_.size() < cap_ || closed_; });
+    if (closed_) return false;
+    q_.push_back(std::move(v));
+    not_empty_.notify_one();
+    return true;
+  }
+  bool pop(T &out) {
+    std::unique_lock<std::mutex> lk(m_);
+    not_empty_.wait(lk, [&] { return !q_.empty() || closed_; });
+    if (q_.empty()) return false;
+    out = std::move(q_.front());
+    q_.pop_front();
+    not_full_.notify_one();
+    return true;
+  }
+  void close() {
+    std::lock_guard<std::mutex> lk(m_);
+    closed_ = true;
+    not_empty_.notify_all();
+    not_full_.notify_all();
+  }
+
+ private:
+  std::mutex m_;
+  std::condition_variable not_full_, not_empty_;
+  std::deque<T> q_;
+  size_t cap_;
+  bool closed_ = false;
+};
+
+/* ------------------------------------------------------------------ */
+/* input: plain / gzip through zlib, bzip2 through `bzip2 -dc`          */
+
+static int spawn_filter(const std::vector<std::string> &argv, int stdin_fd, int stdout_fd, pid_t *pid) {
+  posix_spawn_file_actions_t fa;
+  posix_spawn_file_actions_init(&fa);
+  if (stdin_fd >= 0) posix_spawn_file_actions_adddup2(&fa, stdin_fd, 0);
+  if (stdout_fd >= 0) posix_spawn_file_actions_adddup2(&fa, stdout_fd, 1);
+  std::vector<char *> av;
+  for (auto &a : argv) av.push_back(const_cast<char *>(a.c_str()));
+  av.push_back(nullptr);
+  int rc = posix_spawnp(pid, av[0], &fa, nullptr, av.data(), environ);
+  posix_spawn_file_actions_destroy(&fa);
+  return rc;
+}
+
+class InputStream {
+ public:
+  ~InputStream() { close(); }
+  bool open(const std::string &path, std::string &err) {
+    FILE *f = fopen(path.c_str(), "rb");
+    if (!f) {
+      err = "cannot open " + path;
+      return false;
+    }
+    unsigned char magic[6] = {0};
+    size_t n = fread(magic, 1, sizeof magic, f);
+    fclose(f);
+    if (n >= 3 && magic[0] == 'B' && magic[1] == 'Z' && magic[2] == 'h') {
+      int fds[2];
+      if (pipe2(fds, O_CLOEXEC)) {
+        err = "pipe failed";
+        return false;
+      }
+      int in = ::open(path.c_str(), O_RDONLY | O_CLOEXEC);
+      if (in < 0 || spawn_filter({"bzip2", "-dc"}, in, fds[1], &pid_) != 0) {
+        err = "cannot run bzip2 to read " + path;
+        if (in >= 0) ::close(in);
+        ::close(fds[0]);
+        ::close(fds[1]);
+        return false;
+      }
+      ::close(in);
+      ::close(fds[1]);
+      pipe_ = fdopen(fds[0], "rb");
+      return pipe_ != nullptr;
+    }
+    if (n >= 6 && magic[0] == 0xFD && !memcmp(magic + 1, "7zXZ", 4)) {
+      err = path + ": xz-compressed input is not supported (kraken2 reads plain, gzip and bzip2)";
+      return false;
+    }
+    if (n >= 4 && magic[0] == 0x28 && magic[1] == 0xB5 && magic[2] == 0x2F && magic[3] == 0xFD) {
+      err = path + ": zstd-compressed input is not supported (kraken2 reads plain, gzip and bzip2)";
+      return false;
+    }
+    gz_ = gzopen(path.c_str(), "rb"); /* transparent for uncompressed files */
+    if (!gz_) {
+      err = "cannot open " + path;
+      return false;
+    }
+    gzbuffer(gz_, 1u << 20);
+    return true;
+  }
+  /* returns bytes read, 0 at EOF, -1 on error */
+  long read(char *buf, size_t n) {
+    if (gz_) {
+      int r = gzread(gz_, buf, (unsigned)n);
+      return r;
+    }
+    if (pipe_) {
+      size_t r = fread(buf, 1, n, pipe_);
+      if (r == 0 && ferror(pipe_)) return -1;
+      return (long)r;
+    }
+    return -1;
+  }
+  void close() {
+    if (gz_) gzclose(gz_), gz_ = nullptr;
+    if (pipe_) fclose(pipe_), pipe_ = nullptr;
+    if (pid_ > 0) {
+      int st;
+      waitpid(pid_, &st, 0);
+      pid_ = -1;
+    }
+  }
+
+ private:
+  gzFile gz_ = nullptr;
+  FILE *pipe_ = nullptr;
+  pid_t pid_ = -1;
+};
+
+/* ------------------------------------------------------------------ */
+/* records                                                             */
+
+struct Rec {
+  uint32_t hdr_off, hdr_len;   /* full header line incl. '@' / '>' */
+  uint32_t seq_off, seq_len;
+  uint32_t qual_off, qual_len; /* FASTQ only */
+};
+
+struct Chunk {
+  std::string text; /* arena the records point into */
+  std::vector<Rec> recs;
+  uint64_t bases = 0;
+  bool fastq = true;
+  bool last = false;
+  std::string error;
+};
+
+class RecordReader {
+ public:
+  bool open(const std::string &path, std::string &err) {
+    path_ = path;
+    buf_.resize(4u << 20);
+    return in_.open(path, err);
+  }
+  /* fills `c` with up to NH_CHUNK_RECORDS records; c.last set at EOF */
+  void next_chunk(Chunk &c) {
+    c.text.clear();
+    c.recs.clear();
+    c.bases = 0;
+    c.error.clear();
+    c.last = false;
+    c.text.reserve(24u << 20);
+    c.recs.reserve(NH_CHUNK_RECORDS);
+    while (c.recs.size() < NH_CHUNK_RECORDS) {
+      if (format_ == 0) {
+        int ch = peek();
+        if (ch < 0) {
+          c.last = true;
+          break;
+        }
+        if (ch == '@')
+          format_ = 'q';
+        else if (ch == '>')
+          format_ = 'a';
+        else {
+          c.error = path_ + ": sequence format not recognised (first byte is neither '@' nor '>')";
+          c.last = true;
+          break;
+        }
+      }
+      c.fastq = format_ == 'q';
+      Rec r{};
+      if (format_ == 'q') {
+        std::string *t = &c.text;
+        size_t h0 = t->size();
+        if (!getline_strip(*t)) {
+          c.last = true;
+          break;
+        }
+        r.hdr_off = (uint32_t)h0;
+        r.hdr_len = (uint32_t)(t->size() - h0);
+        if (r.hdr_len == 0) { /* kraken2 stops at an empty header line */
+          t->resize(h0);
+          c.last = true;
+          break;
+        }
+        if ((*t)[h0] != '@') {
+          c.error = path_ + ": malformed FASTQ file (exp. '@', saw \"" + t->substr(h0, 20) + "\")";
+          c.last = true;
+          break;
+        }
+        size_t s0 = t->size();
+        getline_strip(*t);
+        r.seq_off = (uint32_t)s0;
+        r.seq_len = (uint32_t)(t->size() - s0);
+        size_t p0 = t->size();
+        getline_strip(*t); /* '+' line: dropped, kraken2 prints a bare '+' */
+        t->resize(p0);
+        size_t q0 = t->size();
+        getline_strip(*t);
+        r.qual_off = (uint32_t)q0;
+        r.qual_len = (uint32_t)(t->size() - q0);
+      } else {
+        std::string *t = &c.text;
+        size_t h0 = t->size();
+        if (!getline_strip(*t)) {
+          c.last = true;
+          break;
+        }
+        r.hdr_off = (uint32_t)h0;
+        r.hdr_len = (uint32_t)(t->size() - h0);
+        if (r.hdr_len == 0) {
+          t->resize(h0);
+          c.last = true;
+          break;
+        }
+        if ((*t)[h0] != '>') {
+          c.error = path_ + ": malformed FASTA file (exp. '>', saw \"" + t->substr(h0, 20) + "\")";
+          c.last = true;
+          break;
+        }
+        size_t s0 = t->size();
+        for (;;) { /* sequence lines up to the next '>' or EOF, joined */
+          int ch = peek();
+          if (ch < 0 || ch == '>') break;
+          getline_strip(*t);
+        }
+        r.seq_off = (uint32_t)s0;
+        r.seq_len = (uint32_t)(t->size() - s0);
+      }
+      c.bases += r.seq_len;
+      c.recs.push_back(r);
+      if (c.text.size() > (3u << 30)) break; /* keep 32-bit offsets valid */
+    }
+    if (io_error_) c.error = path_ + ": read error (truncated or corrupt compressed stream?)";
+  }
+
+ private:
+  bool fill() {
+    if (eof_) return false;
+    long n = in_.read(&buf_[0], buf_.size());
+    if (n < 0) {
+      io_error_ = true;
+      eof_ = true;
+      return false;
+    }
+    if (n == 0) {
+      eof_ = true;
+      return false;
+    }
+    pos_ = 0;
+    end_ = (size_t)n;
+    return true;
+  }
+  int peek() {
+    if (pos_ >= end_ && !fill()) return -1;
+    return (unsigned char)buf_[pos_];
+  }
+  /* appends the next line without its terminator and trailing whitespace; false at EOF with nothing read */
+  bool getline_strip(std::string &out) {
+    size_t start = out.size();
+    bool any = false;
+    for (;;) {
+      if (pos_ >= end_ && !fill()) break;
+      any = true;
+      const char *p = &buf_[pos_];
+      const char *nl = (const char *)memchr(p, '\n', end_ - pos_);
+      if (nl) {
+        out.append(p, nl - p);
+        pos_ += (size_t)(nl - p) + 1;
+        break;
+      }
+      out.append(p, end_ - pos_);
+      pos_ = end_;
+    }
+    size_t e = out.size();
+    while (e > start && isspace((unsigned char)out[e - 1])) e--;
+    out.resize(e);
+    return any;
+  }
+
+  InputStream in_;
+  std::string path_;
+  std::string buf_;
+  size_t pos_ = 0, end_ = 0;
+  bool eof_ = false, io_error_ = false;
+  int format_ = 0;
+};
+
+/* ------------------------------------------------------------------ */
+/* output: ordered block compression                                    */
+
+typedef size_t (*zstd_bound_fn)(size_t);
+typedef size_t (*zstd_compress_fn)(void *, size_t, const void *, size_t, int);
+typedef unsigned (*zstd_iserror_fn)(size_t);
+
+struct ZstdLib {
+  void *h = nullptr;
+  zstd_bound_fn bound = nullptr;
+  zstd_compress_fn compress = nullptr;
+  zstd_iserror_fn is_error = nullptr;
+  bool load() {
+    if (h) return true;
+    h = dlopen("libzstd.so.1", RTLD_NOW);
+    if (!h) return false;
+    bound = (zstd_bound_fn)dlsym(h, "ZSTD_compressBound");
+    compress = (zstd_compress_fn)dlsym(h, "ZSTD_compress");
+    is_error = (zstd_iserror_fn)dlsym(h, "ZSTD_isError");
+    return bound && compress && is_error;
+  }
+};
+
+static bool gzip_member(const std::string &in, std::string &out) {
+  z_stream zs;
+  memset(&zs, 0, sizeof zs);
+  /* level 6 = the default level flate2/gzp use in the reference (src/compression.rs:214-234) */
+  if (deflateInit2(&zs, 6, Z_DEFLATED, 15 + 16, 8, Z_DEFAULT_STRATEGY) != Z_OK) return false;
+  out.resize(deflateBound(&zs, in.size()) + 32);
+  zs.next_in = (Bytef *)in.data();
+  zs.avail_in = (uInt)in.size();
+  zs.next_out = (Bytef *)&out[0];
+  zs.avail_out = (uInt)out.size();
+  int rc = deflate(&zs, Z_FINISH);
+  size_t n = zs.total_out;
+  deflateEnd(&zs);
+  if (rc != Z_STREAM_END) return false;
+  out.resize(n);
+  return true;
+}
+
+/* One output file.  Blocks are compressed by a shared pool and written in
+ * submission order.  'u': straight write; 'g': gzip members; 'z': zstd frames;
+ * 'b' / 'x': piped through bzip2 / xz (their libraries have no headers here). */
+class OutputFile {
+ public:
+  bool open(const std::string &path, int format, int threads, std::string &err) {
+    path_ = path;
+    format_ = format;
+    if (format == 'b' || format == 'x') {
+      int out = ::open(path.c_str(), O_WRONLY | O_CREAT | O_TRUNC | O_CLOEXEC, 0644);
+      int fds[2];
+      if (out < 0 || pipe2(fds, O_CLOEXEC)) {
+        err = "cannot create " + path;
+        return false;
+      }
+      std::vector<std::string> av = format == 'b' ? std::vector<std::string>{"bzip2", "-c"}
+                                                  : std::vector<std::string>{"xz", "-c", "-6", "-T", std::to_string(threads < 1 ? 1 : threads)};
+      if (spawn_filter(av, fds[0], out, &pid_) != 0) {
+        err = "cannot run " + av[0];
+        return false;
+      }
+      ::close(out);
+      ::close(fds[0]);
+      f_ = fdopen(fds[1], "wb");
+    } else {
+      if (format == 'z' && !zstd_.load()) {
+        err = "zstd output requested but libzstd.so.1 could not be loaded";
+        return false;
+      }
+      f_ = fopen(path.c_str(), "wb");
+    }
+    if (!f_) {
+      err = "cannot create " + path;
+      return false;
+    }
+    setvbuf(f_, nullptr, _IOFBF, 1u << 20);
+    return true;
+  }
+  bool parallel() const { return format_ == 'g' || format_ == 'z'; }
+  bool compress_block(const std::string &in, std::string &out) {
+    if (format_ == 'g') return gzip_member(in, out);
+    if (format_ == 'z') {
+      out.resize(zstd_.bound(in.size()));
+      size_t n = zstd_.compress(&out[0], out.size(), in.data(), in.size(), 3);
+      if (zstd_.is_error(n)) return false;
+      out.resize(n);
+      return true;
+    }
+    return false;
+  }
+  bool write(const std::string &s) { return s.empty() || fwrite(s.data(), 1, s.size(), f_) == s.size(); }
+  bool close() {
+    bool ok = true;
+    if (f_) ok = fclose(f_) == 0, f_ = nullptr;
+    if (pid_ > 0) {
+      int st = 0;
+      waitpid(pid_, &st, 0);
+      ok = ok && WIFEXITED(st) && WEXITSTATUS(st) == 0;
+      pid_ = -1;
+    }
+    return ok;
+  }
+  const std::string &path() const { return path_; }
+
+ private:
+  std::string path_;
+  int format_ = 'u';
+  FILE *f_ = nullptr;
+  pid_t pid_ = -1;
+  ZstdLib zstd_;
+};
+
+struct Block {
+  int file = 0;
+  std::string raw, packed;
+  bool done = false;
+};
+
+class BlockWriter {
+ public:
+  BlockWriter(OutputFile *files, int n_files, int threads) : files_(files), n_files_(n_files) {
+    int n = threads < 1 ? 1 : threads;
+    for (int i = 0; i < n; i++) workers_.emplace_back([this] { work(); });
+    flusher_ = std::thread([this] { flush(); });
+  }
+  void submit(int file, std::string &&raw) {
+    if (raw.empty()) return;
+    auto b = std::make_shared<Block>();
+    b->file = file;
+    b->raw = std::move(raw);
+    std::unique_lock<std::mutex> lk(m_);
+    space_.wait(lk, [&] { return order_.size() < 64; });
+    order_.push_back(b);
+    if (files_[file].parallel())
+      todo_.push_back(b);
+    else
+      b->done = true;
+    cv_.notify_all();
+  }
+  bool finish() {
+    {
+      std::lock_guard<std::mutex> lk(m_);
+      closing_ = true;
+      cv_.notify_all();
+    }
+    for (auto &t : workers_) t.join();
+    flusher_.join();
+    return ok_;
+  }
+
+ private:
+  void work() {
+    for (;;) {
+      std::shared_ptr<Block> b;
+      {
+        std::unique_lock<std::mutex> lk(m_);
+        cv_.wait(lk, [&] { return !todo_.empty() || closing_; });
+        if (todo_.empty()) return;
+        b = todo_.front();
+        todo_.pop_front();
+      }
+      bool ok = files_[b->file].compress_block(b->raw, b->packed);
+      std::lock_guard<std::mutex> lk(m_);
+      if (!ok) ok_ = false;
+      b->raw.clear();
+      b->raw.shrink_to_fit();
+      b->done = true;
+      cv_.notify_all();
+    }
+  }
+  void flush() {
+    for (;;) {
+      std::shared_ptr<Block> b;
+      {
+        std::unique_lock<std::mutex> lk(m_);
+        cv_.wait(lk, [&] { return (!order_.empty() && order_.front()->done) || (closing_ && order_.empty()); });
+        if (order_.empty()) return;
+        b = order_.front();
+        order_.pop_front();
+        space_.notify_all();
+      }
+      const std::string &s = files_[b->file].parallel() ? b->packed : b->raw;
+      if (!files_[b->file].write(s)) {
+        std::lock_guard<std::mutex> lk(m_);
+        ok_ = false;
+      }
+    }
+  }
+  OutputFile *files_;
+  int n_files_;
+  std::mutex m_;
+  std::condition_variable cv_, space_;
+  std::deque<std::shared_ptr<Block>> order_, todo_;
+  std::vector<std::thread> workers_;
+  std::thread flusher_;
+  bool closing_ = false;
+  bool ok_ = true;
+};
+
+/* ------------------------------------------------------------------ */
+/* the pipeline                                                        */
+
+struct Work {
+  uint64_t id = 0;
+  Chunk c[2];
+  uint64_t n_units = 0;
+  std::vector<uint32_t> call;
+  std::vector<uint8_t> keep;
+  std::string error;
+};
+
+/* source of classification decisions: the GPU session, or (host-logic tests) fixed arrays */
+struct Decider {
+  nh_db *db = nullptr;
+  nh_params_t params{};
+  const uint8_t *fixed_keep = nullptr;
+  const uint32_t *fixed_call = nullptr;
+  uint64_t fixed_n = 0;
+};
+
+static void append_record(std::string &out, const Chunk &c, const Rec &r, bool tagged, uint32_t ext) {
+  out.append(c.text, r.hdr_off, r.hdr_len);
+  if (tagged) {
+    char tag[48];
+    int n = snprintf(tag, sizeof tag, " kraken:taxid|%u", ext);
+    out.append(tag, (size_t)n);
+  }
+  out.push_back('\n');
+  out.append(c.text, r.seq_off, r.seq_len);
+  out.push_back('\n');
+  if (c.fastq) {
+    out.append("+\n", 2);
+    out.append(c.text, r.qual_off, r.qual_len);
+    out.push_back('\n');
+  }
+}
+
+static int run_pipeline(const Decider &dec, const nh_files_t *files, nh_run_stats_t *stats) {
+  const auto t0 = std::chrono::steady_clock::now();
+  const bool paired = files->in2 != nullptr;
+  const int nf = paired ? 2 : 1;
+  if (!files->in1 || !files->out1 || (paired && !files->out2))
+    return nh_set_error(NH_ERR_INVALID, "nh_run_files: in1/out1 (and out2 for paired input) are required");
+  if ((files->kraken_output && strcmp(files->kraken_output, "/dev/null") != 0) || files->kraken_report)
+    return nh_set_error(NH_ERR_UNSUPPORTED, "--kraken-output / --kraken-report are not produced by this build");
+  int fmt = files->out_format ? files->out_format : 'u';
+  if (!strchr("ugbxz", fmt)) return nh_set_error(NH_ERR_INVALID, "unknown output format '%c'", fmt);
+  const int threads = dec.params.threads < 1 ? 1 : dec.params.threads;
+  const bool keep_human = dec.params.keep_human != 0;
+
+  std::string err;
+  RecordReader readers[2];
+  if (!readers[0].open(files->in1, err) || (paired && !readers[1].open(files->in2, err)))
+    return nh_set_error(NH_ERR_IO, "%s", err.c_str());
+  OutputFile outs[2];
+  /* like src/main.rs:342-346: one output gets all the threads, two share them */
+  const int per_file_threads = paired ? (threads / 2 < 1 ? 1 : threads / 2) : threads;
+  if (!outs[0].open(files->out1, fmt, per_file_threads, err) ||
+      (paired && !outs[1].open(files->out2, fmt, per_file_threads, err)))
+    return nh_set_error(NH_ERR_IO, "%s", err.c_str());
+
+  /* readers */
+  Channel<std::unique_ptr<Chunk>> chunks[2] = {Channel<std::unique_ptr<Chunk>>(3), Channel<std::unique_ptr<Chunk>>(3)};
+  std::vector<std::thread> reader_threads;
+  for (int f = 0; f < nf; f++)
+    reader_threads.emplace_back([&, f] {
+      for (;;) {
+        auto c = std::make_unique<Chunk>();
+        readers[f].next_chunk(*c);
+        bool last = c->last;
+        if (!chunks[f].push(std::move(c)) || last) break;
+      }
+      chunks[f].close();
+    });
+
+  /* classifiers */
+  std::mutex pair_m;
+  uint64_t next_id = 0;
+  bool input_done = false;
+  std::mutex done_m;
+  std::condition_variable done_cv;
+  std::map<uint64_t, std::unique_ptr<Work>> done;
+  bool failed = false;
+  std::string fail_msg;
+  int live_classifiers = 0;
+
+  auto take = [&]() -> std::unique_ptr<Work> {
+    std::lock_guard<std::mutex> lk(pair_m);
+    if (input_done) return nullptr;
+    auto w = std::make_unique<Work>();
+    for (int f = 0; f < nf; f++) {
+      std::unique_ptr<Chunk> c;
+      if (!chunks[f].pop(c)) {
+        input_done = true;
+        return nullptr;
+      }
+      w->c[f] = std::move(*c);
+      if (!w->c[f].error.empty()) w->error = w->c[f].error;
+      if (w->c[f].last) input_done = true;
+    }
+    w->n_units = w->c[0].recs.size();
+    if (paired && w->c[1].recs.size() != w->n_units) {
+      /* kraken2 stops at the end of the shorter file */
+      if (w->c[1].recs.size() < w->n_units) w->n_units = w->c[1].recs.size();
+      input_done = true;
+    }
+    w->id = next_id++;
+    if (input_done)
+      for (int f = 0; f < nf; f++) chunks[f].close();
+    return w;
+  };
+
+  const int n_classifiers = dec.fixed_keep ? 1 : 2;
+  live_classifiers = n_classifiers;
+  uint64_t fixed_cursor = 0;
+  std::vector<std::thread> classifier_threads;
+  for (int ci = 0; ci < n_classifiers; ci++)
+    classifier_threads.emplace_back([&, ci] {
+      nh_session *sess = nullptr;
+      uint8_t *h_bases = nullptr;
+      uint64_t *h_off = nullptr;
+      size_t cap_bases = 0, cap_seqs = 0;
+      std::string my_err;
+      for (;;) {
+        std::unique_ptr<Work> w = take();
+        if (!w) break;
+        if (w->error.empty() && w->n_units) {
+          const uint64_t n_seqs = w->n_units * nf;
+          uint64_t total = 0;
+          for (int f = 0; f < nf; f++)
+            for (uint64_t i = 0; i < w->n_units; i++) total += w->c[f].recs[i].seq_len;
+          w->call.assign(w->n_units, 0);
+          w->keep.assign(w->n_units, 0);
+          if (dec.fixed_keep) {
+            if (fixed_cursor + w->n_units > dec.fixed_n) {
+              w->error = "fewer decisions than records";
+            } else {
+              memcpy(w->keep.data(), dec.fixed_keep + fixed_cursor, w->n_units);
+              memcpy(w->call.data(), dec.fixed_call + fixed_cursor, w->n_units * 4);
+              fixed_cursor += w->n_units;
+            }
+          } else {
+            if (total + 64 > cap_bases || n_seqs + 1 > cap_seqs) {
+              /* (re)size the session and its pinned staging buffers for this chunk shape */
+              if (sess) nh_session_destroy(sess), sess = nullptr;
+              if (h_bases) nh_host_free(h_bases), h_bases = nullptr;
+              if (h_off) nh_host_free(h_off), h_off = nullptr;
+              cap_bases = (size_t)(total + total / 4) + (1u << 20);
+              cap_seqs = (size_t)NH_CHUNK_RECORDS * nf + 2;
+              nh_params_t p = dec.params;
+              p.max_batch_bases = cap_bases;
+              p.max_batch_seqs = cap_seqs;
+              h_bases = (uint8_t *)nh_host_alloc(cap_bases);
+              h_off = (uint64_t *)nh_host_alloc(cap_seqs * 8);
+              if (!h_bases || !h_off || nh_session_create(dec.db, &p, &sess) != NH_OK) {
+                w->error = std::string("cannot set up a GPU session: ") + nh_last_error();
+                sess = nullptr;
+              }
+            }
+            if (w->error.empty()) {
+              uint64_t o = 0, s = 0;
+              for (uint64_t i = 0; i < w->n_units; i++)
+                for (int f = 0; f < nf; f++) { /* mates interleaved: sequences 2i, 2i+1 */
+                  const Rec &r = w->c[f].recs[i];
+                  h_off[s++] = o;
+                  memcpy(h_bases + o, w->c[f].text.data() + r.seq_off, r.seq_len);
+                  o += r.seq_len;
+                }
+              h_off[s] = o;
+              if (nh_classify_batch(sess, h_bases, h_off, n_seqs, w->call.data(), w->keep.data(), nullptr) != NH_OK)
+                w->error = std::string("classification failed: ") + nh_last_error();
+            }
+          }
+        }
+        std::lock_guard<std::mutex> lk(done_m);
+        done[w->id] = std::move(w);
+        done_cv.notify_all();
+      }
+      if (sess) nh_session_destroy(sess);
+      if (h_bases) nh_host_free(h_bases);
+      if (h_off) nh_host_free(h_off);
+      std::lock_guard<std::mutex> lk(done_m);
+      live_classifiers--;
+      done_cv.notify_all();
+    });
+
+  /* writer (this thread): batches in id order */
+  BlockWriter bw(outs, nf, threads);
+  uint64_t want = 0, total_units = 0, n_classified = 0, total_bases = 0;
+  std::string pend[2];
+  for (;;) {
+    std::unique_ptr<Work> w;
+    {
+      std::unique_lock<std::mutex> lk(done_m);
+      done_cv.wait(lk, [&] { return done.count(want) || live_classifiers == 0; });
+      auto it = done.find(want);
+      if (it == done.end()) break;
+      w = std::move(it->second);
+      done.erase(it);
+    }
+    want++;
+    if (!w->error.empty()) {
+      if (!failed) fail_msg = w->error;
+      failed = true;
+    }
+    if (failed) continue; /* drain */
+    for (uint64_t i = 0; i < w->n_units; i++) {
+      const bool classified = w->call[i] != 0;
+      n_classified += classified;
+      if (!w->keep[i]) continue;
+      for (int f = 0; f < nf; f++) {
+        append_record(pend[f], w->c[f], w->c[f].recs[i], classified && files->tag_classified, w->call[i]);
+        if (pend[f].size() >= NH_OUT_BLOCK) {
+          bw.submit(f, std::move(pend[f]));
+          pend[f].clear();
+        }
+      }
+    }
+    total_units += w->n_units;
+    for (int f = 0; f < nf; f++)
+      for (uint64_t i = 0; i < w->n_units; i++) total_bases += w->c[f].recs[i].seq_len;
+  }
+  for (int f = 0; f < nf; f++) bw.submit(f, std::move(pend[f]));
+  for (int f = 0; f < nf; f++) chunks[f].close();
+  for (auto &t : classifier_threads) t.join();
+  for (auto &t : reader_threads) t.join();
+  bool wrote = bw.finish();
+  for (int f = 0; f < nf; f++) wrote = outs[f].close() && wrote;
+  (void)keep_human;
+  if (failed) return nh_set_error(NH_ERR_IO, "%s", fail_msg.c_str());
+  if (!wrote) return nh_set_error(NH_ERR_IO, "writing %s failed", outs[0].path().c_str());
+  if (stats) {
+    stats->total = total_units;
+    stats->classified = n_classified;
+    stats->unclassified = total_units - n_classified;
+    stats->bases = total_bases;
+    stats->seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  }
+  return NH_OK;
+}
+
+}  // namespace
+
+extern "C" int nh_run_files(nh_session *s, const nh_files_t *files, nh_run_stats_t *stats) {
+  if (!s || !files) return nh_set_error(NH_ERR_INVALID, "null argument");
+  Decider d;
+  d.db = s->db;
+  d.params = s->params;
+  d.params.paired = files->in2 != nullptr;
+  return run_pipeline(d, files, stats);
+}
+
+/* Host-logic test hook: the same reader -> writer -> compressor pipeline with
+ * the per-unit decisions supplied by the caller instead of the GPU. */
+extern "C" int nh_debug_rewrite_files(const nh_files_t *files, const uint8_t *keep, const uint32_t *call_ext,
+                                      uint64_t n_units, int threads, nh_run_stats_t *stats) {
+  if (!files || !keep || !call_ext) return nh_set_error(NH_ERR_INVALID, "null argument");
+  Decider d;
+  d.params.threads = threads;
+  d.params.paired = files->in2 != nullptr;
+  d.fixed_keep = keep;
+  d.fixed_call = call_ext;
+  d.fixed_n = n_units;
+  return run_pipeline(d, files, stats);
+}

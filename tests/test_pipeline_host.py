@@ -1,0 +1,191 @@
+"""Host logic of the file API (reader -> ordered writer -> block compressor),
+driven through the C ABI with caller-supplied decisions (nh_debug_rewrite_files),
+so it runs without a GPU.  Expected bytes are written here from the kraken2
+output rules: header\\nseq\\n+\\nquals\\n, trailing whitespace
+stripped, FASTA joined, classified records tagged " kraken:taxid|N"."""
+import bz2
+import gzip
+import lzma
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+import synth
+from nohuman_b200 import NhError
+from nohuman_b200.api import rewrite_files
+
+
+def make_records(n, seed, fasta=False, messy=False):
+    rng = np.random.default_rng(seed)
+    recs = []
+    for i in range(n):
+        L = int(rng.integers(1, 400))
+        seq = bytes(synth.random_genome(rng, L))
+        qual = bytes(rng.integers(33, 74, size=L, dtype=np.uint8))
+        hdr = (b">" if fasta else b"@") + f"read{i} extra=words {i * 7}".encode()
+        recs.append((hdr, seq, qual))
+    return recs
+
+
+def write_input(path, recs, fasta=False, messy=False, comp=None):
+    out = bytearray()
+    for i, (h, s, q) in enumerate(recs):
+        if fasta:
+            out += h + (b"  \r\n" if messy else b"\n")
+            w = 60 if messy else max(1, len(s))
+            for k in range(0, len(s), w):
+                out += s[k:k + w] + b"\n"
+        else:
+            out += h + (b" \t\r\n" if messy and i % 3 == 0 else b"\n")
+            out += s + (b"\r\n" if messy and i % 5 == 0 else b"\n")
+            out += (b"+" + h[1:] if messy and i % 2 == 0 else b"+") + b"\n"
+            out += q + b"\n"
+    data = bytes(out)
+    if comp == "gz":
+        data = gzip.compress(data)
+    elif comp == "bz2":
+        data = bz2.compress(data)
+    with open(path, "wb") as f:
+        f.write(data)
+
+
+def expected(recs, keep, call, fasta=False, tag=True):
+    out = bytearray()
+    for (h, s, q), k, c in zip(recs, keep, call):
+        if not k:
+            continue
+        hh = h.rstrip()
+        if c and tag:
+            hh += b" kraken:taxid|%d" % c
+        out += hh + b"\n" + s + b"\n"
+        if not fasta:
+            out += b"+\n" + q + b"\n"
+    return bytes(out)
+
+
+def read_output(path, fmt):
+    raw = open(path, "rb").read()
+    if fmt == "g":
+        assert raw[:2] == b"\x1f\x8b"
+        return gzip.decompress(raw)  # handles concatenated members
+    if fmt == "b":
+        assert raw[:3] == b"BZh"
+        return bz2.decompress(raw)
+    if fmt == "x":
+        assert raw[:6] == b"\xfd7zXZ\x00"
+        return lzma.decompress(raw)
+    if fmt == "z":
+        assert raw[:4] == b"\x28\xb5\x2f\xfd"
+        import ctypes as C
+        z = C.CDLL("libzstd.so.1")
+        z.ZSTD_decompressStream  # present
+        # frame-by-frame with the simple API
+        z.ZSTD_findFrameCompressedSize.restype = C.c_size_t
+        z.ZSTD_findFrameCompressedSize.argtypes = [C.c_char_p, C.c_size_t]
+        z.ZSTD_getFrameContentSize.restype = C.c_ulonglong
+        z.ZSTD_getFrameContentSize.argtypes = [C.c_char_p, C.c_size_t]
+        z.ZSTD_decompress.restype = C.c_size_t
+        z.ZSTD_decompress.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t]
+        out, pos = bytearray(), 0
+        while pos < len(raw):
+            chunk = raw[pos:]
+            n = z.ZSTD_findFrameCompressedSize(chunk, len(chunk))
+            size = z.ZSTD_getFrameContentSize(chunk, n)
+            buf = C.create_string_buffer(size)
+            got = z.ZSTD_decompress(buf, size, chunk, n)
+            assert got == size
+            out += buf.raw[:size]
+            pos += n
+        return bytes(out)
+    return raw
+
+
+@pytest.mark.parametrize("fmt", ["u", "g", "b", "x", "z"])
+def test_single_end_formats(tmp_path, fmt):
+    if fmt == "b" and not shutil.which("bzip2") or fmt == "x" and not shutil.which("xz"):
+        pytest.skip("compressor CLI missing")
+    recs = make_records(5000, seed=1)
+    rng = np.random.default_rng(2)
+    keep = rng.integers(0, 2, size=len(recs), dtype=np.uint8)
+    call = np.where(keep == 0, 9606, 0).astype(np.uint32)  # default mode: kept == unclassified
+    inp, out = tmp_path / "in.fq", tmp_path / f"out.{fmt}"
+    write_input(inp, recs)
+    st = rewrite_files(keep, call, inp, out, out_format=fmt, threads=3)
+    assert (st.total, st.classified, st.unclassified) == (5000, int((call != 0).sum()), int((call == 0).sum()))
+    assert st.bases == sum(len(s) for _, s, _ in recs)
+    assert read_output(out, fmt) == expected(recs, keep, call)
+
+
+@pytest.mark.parametrize("comp", [None, "gz", "bz2"])
+def test_paired_keep_human_tags_and_messy_input(tmp_path, comp):
+    n = 70000  # more than one reader chunk (65536 records)
+    r1, r2 = make_records(n, seed=3), make_records(n, seed=4)
+    rng = np.random.default_rng(5)
+    call = np.where(rng.random(n) < 0.5, 9606, 0).astype(np.uint32)
+    call[::11] = np.where(call[::11] != 0, 131567, 0)
+    keep = (call != 0).astype(np.uint8)  # -H: kept == classified
+    ext = {None: "", "gz": ".gz", "bz2": ".bz2"}[comp]
+    i1, i2 = tmp_path / f"a_1.fq{ext}", tmp_path / f"a_2.fq{ext}"
+    write_input(i1, r1, messy=True, comp=comp)
+    write_input(i2, r2, messy=True, comp=comp)
+    o1, o2 = tmp_path / "o1.fq.gz", tmp_path / "o2.fq.gz"
+    st = rewrite_files(keep, call, i1, o1, i2, o2, out_format="g", threads=4)
+    assert st.total == n and st.classified == int(keep.sum())
+    assert read_output(o1, "g") == expected(r1, keep, call)
+    assert read_output(o2, "g") == expected(r2, keep, call)
+    # the gzip output is multi-member (one member per block) and plain gunzip reads it
+    assert subprocess.run(["gzip", "-t", str(o1)]).returncode == 0
+    assert open(o1, "rb").read().count(b"\x1f\x8b\x08") >= 2
+
+
+def test_fasta_multiline_is_joined(tmp_path):
+    recs = make_records(300, seed=6, fasta=True)
+    keep = np.ones(len(recs), np.uint8)
+    call = np.zeros(len(recs), np.uint32)
+    inp, out = tmp_path / "in.fa", tmp_path / "out.fq"
+    write_input(inp, recs, fasta=True, messy=True)
+    rewrite_files(keep, call, inp, out)
+    assert open(out, "rb").read() == expected(recs, keep, call, fasta=True)
+
+
+def test_paired_stops_at_shorter_file_and_empty_input(tmp_path):
+    r1, r2 = make_records(100, seed=7), make_records(60, seed=8)
+    i1, i2 = tmp_path / "x_1.fq", tmp_path / "x_2.fq"
+    write_input(i1, r1)
+    write_input(i2, r2)
+    keep = np.ones(100, np.uint8)
+    call = np.zeros(100, np.uint32)
+    o1, o2 = tmp_path / "o1.fq", tmp_path / "o2.fq"
+    st = rewrite_files(keep, call, i1, o1, i2, o2)
+    assert st.total == 60
+    assert open(o1, "rb").read() == expected(r1[:60], keep, call)
+    assert open(o2, "rb").read() == expected(r2, keep, call)
+    # empty input: zero records, empty output, no error
+    e = tmp_path / "empty.fq"
+    e.write_bytes(b"")
+    st = rewrite_files(keep, call, e, tmp_path / "oe.fq")
+    assert st.total == 0 and os.path.getsize(tmp_path / "oe.fq") == 0
+
+
+def test_errors(tmp_path):
+    keep, call = np.ones(4, np.uint8), np.zeros(4, np.uint32)
+    with pytest.raises(NhError) as ei:
+        rewrite_files(keep, call, tmp_path / "missing.fq", tmp_path / "o.fq")
+    assert "cannot open" in ei.value.message
+    bad = tmp_path / "bad.txt"
+    bad.write_bytes(b"hello world\n")
+    with pytest.raises(NhError) as ei:
+        rewrite_files(keep, call, bad, tmp_path / "o.fq")
+    assert "format not recognised" in ei.value.message
+    xz = tmp_path / "in.fq.xz"
+    xz.write_bytes(lzma.compress(b"@r\nACGT\n+\nIIII\n"))
+    with pytest.raises(NhError) as ei:
+        rewrite_files(keep, call, xz, tmp_path / "o.fq")
+    assert "xz-compressed input is not supported" in ei.value.message
+    ok = tmp_path / "ok.fq"
+    ok.write_bytes(b"@r\nACGT\n+\nIIII\n")
+    with pytest.raises(NhError):
+        rewrite_files(keep, call, ok, tmp_path / "o.fq", out_format="q")
