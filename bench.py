@@ -231,41 +231,30 @@ def main():
     if use_dist:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    # ---------------- database: built on rank 0, broadcast over NCCL ----------------
+    # ---------------- database: built on rank 0, replicated over NCCL/NVLink ----------------
+    from nohuman_b200 import dist as nhd
     capacity = 1 << args.capacity_log2
     t_build0 = time.perf_counter()
-    nodes, leaves = synth.human_pangenome_taxonomy()
-    taxo_b, internal = synth.taxonomy_image(nodes)
-    opts_b = synth.opts_image()
     sdb = None
+    cells = hdr = opts_b = taxo_b = None
+    gmeta = torch.zeros(1, dtype=torch.int64, device="cuda")
     if rank == 0:
         sdb = synth.build_synthetic_db(capacity, device=dev)
-        meta = torch.tensor([sdb.genome_bases, sdb.db.info.size, sdb.db.info.key_bits,
-                             sdb.db.info.value_bits], dtype=torch.int64, device="cuda")
-    else:
-        meta = torch.zeros(4, dtype=torch.int64, device="cuda")
+        opts_b, taxo_b = sdb.opts, sdb.taxo
+        hdr = sdb.hash_header()
+        gmeta[0] = sdb.genome_bases
+        db = sdb.db
     keep_alive = None
     if use_dist:
-        dist.broadcast(meta, 0)
-        nbytes = ((capacity + 31) // 32) * 128
+        dist.broadcast(gmeta, 0)
         if rank == 0:
-            table = torch.as_tensor(DevPtr(sdb.db.device_cells_ptr(), nbytes), device="cuda")
-        else:
-            table = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
-        dist.broadcast(table, 0)
+            cells = torch.as_tensor(DevPtr(sdb.db.device_cells_ptr(), nhd.padded_cells(capacity) * 4), device="cuda")
+        cells, hdr, opts_b, taxo_b = nhd.broadcast_table(cells, hdr, opts_b, taxo_b, torch.device("cuda", dev))
         torch.cuda.synchronize()
         if rank != 0:
-            keep_alive = table
-            hdr = [capacity, int(meta[1]), int(meta[2]), int(meta[3])]
-            db = Database.from_memory(opts_b, taxo_b, hdr, table.data_ptr(), device=dev,
-                                      cells_on_device=True)
-        else:
-            db = sdb.db
-    else:
-        db = sdb.db
-    m = meta.cpu().numpy()
-    sdb_meta = {"genome_seed": 0x5EED, "genome_bases": int(m[0])}
-    hdr = [capacity, int(m[1]), int(m[2]), int(m[3])]
+            keep_alive = cells
+            db = Database.from_memory(opts_b, taxo_b, hdr, cells.data_ptr(), device=dev, cells_on_device=True)
+    sdb_meta = {"genome_seed": 0x5EED, "genome_bases": int(gmeta.item())}
     t_build = time.perf_counter() - t_build0
 
     n_pairs = args.pairs_per_step
