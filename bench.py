@@ -357,10 +357,21 @@ def main():
     dom = max(stage, key=lambda k_: stage[k_])
     probe_name = "scan_probe_score" if fused else "probe"
 
+    traffic_tab = {}
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            tj = json.load(f)
+        w = tj.get("workload", {})
+        if (w.get("pairs_per_step_per_gpu") == n_pairs and w.get("table_cells") == capacity
+                and w.get("read_len") == READ_LEN):
+            traffic_tab = tj
+
     def roof(kname):
         ach = alg[kname] / (stage[kname] * 1e-3) / 1e9 if stage[kname] > 0 else 0.0
+        tr = traffic_tab.get("k_" + kname, {}).get("dram_bytes_per_launch")
         return {"kernel": "k_" + kname, "bound": "hbm", "achieved": round(ach, 1), "peak": peak,
-                "unit": "GB/s", "frac": round(ach / peak, 4), "traffic": None, "peak_source": peak_src,
+                "unit": "GB/s", "frac": round(ach / peak, 4), "traffic": tr, "peak_source": peak_src,
                 "ms_per_launch": round(stage[kname], 4),
                 "algorithmic_bytes_per_launch": int(alg[kname])}
 
