@@ -121,6 +121,9 @@ int nh_db_open(const char *db_dir, int device, nh_db **out);
 int nh_db_open_memory(const void *opts, size_t opts_len, const void *taxo, size_t taxo_len,
                       const uint64_t hash_header[4], const uint32_t *cells, int cells_on_device,
                       int device, nh_db **out);
+/* Replicate an open database onto another device of this process (peer copy,
+ * NVLink when the devices are connected); the clone is independent of `src`. */
+int nh_db_clone(const nh_db *src, int device, nh_db **out);
 int nh_db_info(const nh_db *db, nh_db_info_t *out);
 /* Device pointer of the resident cell array (for NCCL broadcast by the host). */
 const uint32_t *nh_db_device_cells(const nh_db *db);
@@ -170,6 +173,12 @@ typedef struct {
   const char *kraken_report;  /* --report; NULL: not produced */
 } nh_files_t;
 int nh_run_files(nh_session *s, const nh_files_t *files, nh_run_stats_t *stats);
+/* Same over several sessions, one per GPU with the database replicated
+ * (nh_db_clone): read batches are dealt to the GPUs as they free up, nothing is
+ * exchanged between them, and the writer restores input order.  Parameters
+ * are taken from sessions[0]. */
+int nh_run_files_multi(nh_session *const *sessions, int n_sessions, const nh_files_t *files,
+                       nh_run_stats_t *stats);
 /* Host-logic test hook (no GPU): the same reader -> ordered writer -> block
  * compressor pipeline with the per-unit decisions (keep[], external call[])
  * supplied by the caller. */

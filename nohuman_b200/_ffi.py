@@ -89,6 +89,7 @@ SYMBOLS = {
     "nh_db_open_memory": (_i32, [_vp, C.c_size_t, _vp, C.c_size_t, C.POINTER(_u64), _vp, _i32, _i32,
                                  C.POINTER(_vp)]),
     "nh_db_info": (_i32, [_vp, C.POINTER(DbInfo)]),
+    "nh_db_clone": (_i32, [_vp, _i32, C.POINTER(_vp)]),
     "nh_db_device_cells": (_vp, [_vp]),
     "nh_db_close": (None, [_vp]),
     "nh_session_create": (_i32, [_vp, C.POINTER(Params), C.POINTER(_vp)]),
@@ -97,6 +98,7 @@ SYMBOLS = {
     "nh_classify_batch_device": (_i32, [_vp, _vp, _vp, _u64, _u64, _vp, _vp]),
     "nh_session_sync": (_i32, [_vp, C.POINTER(BatchStats)]),
     "nh_run_files": (_i32, [_vp, C.POINTER(Files), C.POINTER(RunStats)]),
+    "nh_run_files_multi": (_i32, [C.POINTER(_vp), _i32, C.POINTER(Files), C.POINTER(RunStats)]),
     "nh_debug_rewrite_files": (_i32, [C.POINTER(Files), _vp, _vp, _u64, _i32, C.POINTER(RunStats)]),
     "nh_session_stream": (_vp, [_vp]),
     "nh_host_alloc": (_vp, [C.c_size_t]),

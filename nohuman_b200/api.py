@@ -41,6 +41,16 @@ def make_files(in1, out1, in2=None, out2=None, out_format="u", tag_classified=Tr
     return f
 
 
+def run_files_multi(sessions, in1, out1, in2=None, out2=None, out_format="u", tag_classified=True) -> RunStats:
+    """nh_run_files over several sessions (one per GPU, database replicated): batches are
+    dealt to the GPUs, output order is input order."""
+    f = make_files(in1, out1, in2, out2, out_format, tag_classified)
+    arr = (C.c_void_p * len(sessions))(*[s._h for s in sessions])
+    st = RunStats()
+    check(lib().nh_run_files_multi(arr, len(sessions), C.byref(f), C.byref(st)))
+    return st
+
+
 def rewrite_files(keep: np.ndarray, call_ext: np.ndarray, in1, out1, in2=None, out2=None,
                   out_format="u", tag_classified=True, threads=2) -> RunStats:
     """Host-logic test hook (no GPU): the file pipeline with decisions supplied by the caller."""
@@ -80,6 +90,12 @@ class Database:
         check(lib().nh_db_open_memory(opts, len(opts), taxo, len(taxo), hdr, ptr,
                                       int(cells_on_device), device, C.byref(h)))
         return cls(h.value)
+
+    def clone(self, device: int) -> "Database":
+        """Replica on another GPU of this process (peer copy)."""
+        h = C.c_void_p()
+        check(lib().nh_db_clone(self._h, device, C.byref(h)))
+        return Database(h.value)
 
     @property
     def info(self) -> DbInfo:

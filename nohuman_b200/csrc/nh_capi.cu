@@ -385,6 +385,44 @@ extern "C" int nh_db_open(const char *db_dir, int device, nh_db **out) {
   return NH_OK;
 }
 
+extern "C" int nh_db_clone(const nh_db *src, int device, nh_db **out) {
+  if (!src || !out) return nh_set_error(NH_ERR_INVALID, "null argument");
+  int rc = select_device(device);
+  if (rc) return rc;
+  nh_db *db = new nh_db();
+  db->info = src->info;
+  db->info.device = device;
+  db->h_parent = src->h_parent;
+  db->h_ext = src->h_ext;
+  db->h_ext64 = src->h_ext64;
+  const uint64_t cap = src->info.capacity;
+  const size_t bytes = ((cap + 31) / 32) * 128;
+  cudaError_t e = cudaMalloc(&db->d_cells, bytes);
+  if (e != cudaSuccess) {
+    delete db;
+    return nh_set_error(NH_ERR_NOMEM, "cudaMalloc(%zu) for the hash table failed: %s", bytes, cudaGetErrorString(e));
+  }
+  db->owns_cells = true;
+  int can = 0;
+  if (cudaDeviceCanAccessPeer(&can, device, src->info.device) == cudaSuccess && can) {
+    cudaError_t pe = cudaDeviceEnablePeerAccess(src->info.device, 0);
+    if (pe != cudaSuccess) cudaGetLastError(); /* already enabled is fine; the copy works either way */
+  }
+  e = cudaMemcpyPeer(db->d_cells, device, src->d_cells, src->info.device, bytes);
+  if (e != cudaSuccess) {
+    nh_db_close(db);
+    return nh_set_error(NH_ERR_CUDA, "replicating the hash table to device %d failed: %s", device, cudaGetErrorString(e));
+  }
+  const uint64_t hdr[4] = {src->info.capacity, src->info.size, src->info.key_bits, src->info.value_bits};
+  rc = finish_db(db, hdr);
+  if (rc) {
+    nh_db_close(db);
+    return rc;
+  }
+  *out = db;
+  return NH_OK;
+}
+
 extern "C" int nh_db_info(const nh_db *db, nh_db_info_t *out) {
   if (!db || !out) return nh_set_error(NH_ERR_INVALID, "null argument");
   *out = db->info;
@@ -513,7 +551,7 @@ extern "C" void *nh_session_stream(nh_session *s) { return s ? (void *)s->stream
 
 extern "C" void *nh_host_alloc(size_t bytes) {
   void *p = nullptr;
-  if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) {
+  if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) { /* usable from every device */
     cudaGetLastError();
     nh_set_error(NH_ERR_NOMEM, "cudaHostAlloc(%zu) failed", bytes);
     return nullptr;

@@ -568,7 +568,7 @@ struct Work {
 
 /* source of classification decisions: the GPU session, or (host-logic tests) fixed arrays */
 struct Decider {
-  nh_db *db = nullptr;
+  std::vector<nh_db *> dbs; /* one replica per GPU */
   nh_params_t params{};
   const uint8_t *fixed_keep = nullptr;
   const uint32_t *fixed_call = nullptr;
@@ -667,7 +667,8 @@ static int run_pipeline(const Decider &dec, const nh_files_t *files, nh_run_stat
     return w;
   };
 
-  const int n_classifiers = dec.fixed_keep ? 1 : 2;
+  /* two classifier threads per GPU: one batch's copies overlap the other's kernel */
+  const int n_classifiers = dec.fixed_keep ? 1 : 2 * (int)dec.dbs.size();
   live_classifiers = n_classifiers;
   uint64_t fixed_cursor = 0;
   std::vector<std::thread> classifier_threads;
@@ -709,7 +710,7 @@ static int run_pipeline(const Decider &dec, const nh_files_t *files, nh_run_stat
               p.max_batch_seqs = cap_seqs;
               h_bases = (uint8_t *)nh_host_alloc(cap_bases);
               h_off = (uint64_t *)nh_host_alloc(cap_seqs * 8);
-              if (!h_bases || !h_off || nh_session_create(dec.db, &p, &sess) != NH_OK) {
+              if (!h_bases || !h_off || nh_session_create(dec.dbs[(size_t)ci % dec.dbs.size()], &p, &sess) != NH_OK) {
                 w->error = std::string("cannot set up a GPU session: ") + nh_last_error();
                 sess = nullptr;
               }
@@ -801,8 +802,21 @@ static int run_pipeline(const Decider &dec, const nh_files_t *files, nh_run_stat
 extern "C" int nh_run_files(nh_session *s, const nh_files_t *files, nh_run_stats_t *stats) {
   if (!s || !files) return nh_set_error(NH_ERR_INVALID, "null argument");
   Decider d;
-  d.db = s->db;
+  d.dbs.push_back(s->db);
   d.params = s->params;
+  d.params.paired = files->in2 != nullptr;
+  return run_pipeline(d, files, stats);
+}
+
+extern "C" int nh_run_files_multi(nh_session *const *sessions, int n_sessions, const nh_files_t *files,
+                                  nh_run_stats_t *stats) {
+  if (!sessions || n_sessions < 1 || !files) return nh_set_error(NH_ERR_INVALID, "bad argument");
+  Decider d;
+  for (int i = 0; i < n_sessions; i++) {
+    if (!sessions[i]) return nh_set_error(NH_ERR_INVALID, "null session");
+    d.dbs.push_back(sessions[i]->db);
+  }
+  d.params = sessions[0]->params;
   d.params.paired = files->in2 != nullptr;
   return run_pipeline(d, files, stats);
 }

@@ -328,7 +328,8 @@ static void usage() {
        "  -C, --conf <[0, 1]>        Kraken2 minimum confidence score [default: 0.0]\n"
        "  -k, --kraken-output <FILE> Write the Kraken2 read classification output to a file\n"
        "  -r, --kraken-report <FILE> Write the Kraken2 report with aggregate counts/clade to file\n"
-       "      --gpu <ID>             CUDA device to use [default: 0]\n"
+       "      --gpu <ID>             First CUDA device to use [default: 0]\n"
+       "      --gpus <N|all>         Number of GPUs: read batches are sharded, the database is replicated [default: 1]\n"
        "  -v, --verbose              Set the logging level to verbose\n"
        "  -h, --help                 Print help\n"
        "  -V, --version              Print version");
@@ -342,10 +343,11 @@ int main(int argc, char **argv) {
                           {"human", 0, 0, 'H'},        {"conf", 1, 0, 'C'},          {"kraken-output", 1, 0, 'k'},
                           {"kraken-report", 1, 0, 'r'}, {"verbose", 0, 0, 'v'},      {"help", 0, 0, 'h'},
                           {"version", 0, 0, 'V'},      {"gpu", 1, 0, 3},             {"plan", 0, 0, 4},
+                          {"gpus", 1, 0, 5},
                           {0, 0, 0, 0}};
   std::string out1, out2, db, db_version, kraken_output, kraken_report, err;
   bool check = false, download = false, list = false, human = false, plan = false;
-  int out_type = 0, gpu = 0;
+  int out_type = 0, gpu = 0, gpus = 1;
   long threads = 1;
   double conf = 0.0;
   if (const char *e = getenv("NOHUMAN_DB")) db = e;
@@ -379,6 +381,7 @@ int main(int argc, char **argv) {
       case 'h': usage(); return 0;
       case 'V': printf("nohuman 0.5.1 (B200 hot path, libnohuman_gpu ABI %d)\n", nh_abi_version()); return 0;
       case 3: gpu = atoi(optarg); break;
+      case 5: gpus = !strcmp(optarg, "all") ? -1 : atoi(optarg); break;
       case 4: plan = true; break; /* hidden: print what would run (database, format, outputs) and exit */
       default: return 2;
     }
@@ -463,6 +466,19 @@ int main(int argc, char **argv) {
   p.threads = (int)threads;
   nh_session *sess = nullptr;
   if (nh_session_create(dbh, &p, &sess)) return fail("%s", nh_last_error());
+  /* more GPUs: replicate the table once (peer copies), no exchange afterwards */
+  if (gpus < 0) gpus = nh_device_count() - gpu;
+  if (gpus < 1 || gpu + gpus > nh_device_count()) return fail("--gpus %d from device %d: only %d device(s) visible", gpus, gpu, nh_device_count());
+  std::vector<nh_db *> replicas{dbh};
+  std::vector<nh_session *> sessions{sess};
+  for (int g = 1; g < gpus; g++) {
+    nh_db *r = nullptr;
+    nh_session *rs = nullptr;
+    if (nh_db_clone(dbh, gpu + g, &r) || nh_session_create(r, &p, &rs)) return fail("%s", nh_last_error());
+    replicas.push_back(r);
+    sessions.push_back(rs);
+  }
+  if (gpus > 1) logmsg("INFO", "Database replicated on %d GPUs", gpus);
   logmsg("INFO", human ? "Keeping human reads..." : "Removing human reads...");
   nh_files_t f;
   memset(&f, 0, sizeof f);
@@ -476,7 +492,7 @@ int main(int argc, char **argv) {
   f.kraken_report = kraken_report.empty() ? nullptr : kraken_report.c_str();
   nh_run_stats_t st;
   memset(&st, 0, sizeof st);
-  if (nh_run_files(sess, &f, &st)) return fail("Failed to run kraken2: %s", nh_last_error());
+  if (nh_run_files_multi(sessions.data(), (int)sessions.size(), &f, &st)) return fail("Failed to run kraken2: %s", nh_last_error());
   /* the line CommandRunner::run logs from kraken2's stderr (src/lib.rs:38-45) */
   logmsg("INFO", "%llu / %llu (%.2f%%) sequences classified as human; %llu (%.2f%%) as non-human",
          (unsigned long long)st.classified, (unsigned long long)st.total, pct(st.classified, st.total),
@@ -485,8 +501,8 @@ int main(int argc, char **argv) {
   logmsg("INFO", "Output file written to: \"%s\"", out1.c_str());
   if (paired) logmsg("INFO", "Output file written to: \"%s\"", out2.c_str());
   logmsg("DEBUG", "%.3f s, %.2f Mbp", st.seconds, st.bases / 1e6);
-  nh_session_destroy(sess);
-  nh_db_close(dbh);
+  for (auto *x : sessions) nh_session_destroy(x);
+  for (auto *x : replicas) nh_db_close(x);
   logmsg("INFO", "Done.");
   return 0;
 }

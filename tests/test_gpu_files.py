@@ -138,3 +138,33 @@ def test_cli_check_and_errors(small_db, tmp_path):
     bad.write_bytes(b"not a fastq file\n")
     r = subprocess.run([os.path.join(BIN, "nohuman"), "--db", small_db.path, str(bad)], capture_output=True, text=True)
     assert r.returncode != 0 and "format not recognised" in r.stderr
+
+
+def test_replicated_database_and_sharded_batches(small_db, gpu_db, reads, tmp_path):
+    """nh_db_clone + nh_run_files_multi: replicas (on a second GPU when there is one, else on the
+    same device) classify batches dealt to them; output and counts equal the single-session run."""
+    from nohuman_b200 import Session, _ffi
+    from nohuman_b200.api import run_files_multi
+    n_dev = _ffi.lib().nh_device_count()
+    ext = oracle_calls(small_db, reads["pe"], True, 0.5)
+    replica = gpu_db.clone(1 if n_dev > 1 else 0)
+    try:
+        assert replica.info.capacity == gpu_db.info.capacity and replica.info.device == (1 if n_dev > 1 else 0)
+        with Session(gpu_db, confidence=0.5, paired=True, threads=2) as s0, \
+                Session(replica, confidence=0.5, paired=True, threads=2) as s1:
+            # the replica answers like the original
+            keys = np.arange(1, 5000, dtype=np.uint64) * np.uint64(0x9E3779B97F4A7C15)
+            np.testing.assert_array_equal(s0.debug_probe(keys), s1.debug_probe(keys))
+            o1, o2 = str(tmp_path / "m1.fq.gz"), str(tmp_path / "m2.fq.gz")
+            st = run_files_multi([s0, s1], reads["paths"]["m1"], o1, reads["paths"]["m2"], o2, out_format="g")
+        assert (st.total, st.classified) == (len(ext), int((ext != 0).sum()))
+        keep, zero = ext == 0, np.zeros_like(ext)
+        assert gzip.decompress(open(o1, "rb").read()) == expected_fastq(reads["m1"], "p", "/1", keep, zero)
+        assert gzip.decompress(open(o2, "rb").read()) == expected_fastq(reads["m2"], "p", "/2", keep, zero)
+    finally:
+        replica.close()
+    r = subprocess.run([os.path.join(BIN, "nohuman"), "--db", small_db.path, "--gpus", "all", "--conf", "0.5",
+                        "-o", str(tmp_path / "c1.fq"), "-O", str(tmp_path / "c2.fq"),
+                        reads["paths"]["m1"], reads["paths"]["m2"]], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert open(str(tmp_path / "c1.fq"), "rb").read() == expected_fastq(reads["m1"], "p", "/1", ext == 0, np.zeros_like(ext))
