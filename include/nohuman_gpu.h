@@ -74,6 +74,9 @@ typedef struct {
   int32_t threads;            /* host threads for the file API; <=0: 1 */
   uint64_t max_batch_bases;   /* session capacity; 0 selects 256 MiB */
   uint64_t max_batch_seqs;    /* session capacity; 0 selects max_batch_bases/64 */
+  int32_t emit_runs;          /* 1: keep per-sequence (taxid, k-mer count) runs for nh_last_batch_runs
+                                 (kraken2's per-read output, --output; costs 5 B per lookup of D2H) */
+  int32_t reserved;
 } nh_params_t;
 
 typedef struct {
@@ -149,6 +152,14 @@ int nh_classify_batch_device(nh_session *s, const uint8_t *d_bases, const uint64
                              uint64_t n_seqs, uint64_t total_bases, uint32_t *d_out_call,
                              uint8_t *d_out_keep);
 int nh_session_sync(nh_session *s, nh_batch_stats_t *stats);
+/* Per-sequence hit runs of the batch just classified (session created with
+ * emit_runs = 1): sequence i owns runs [seq_first_run[i], seq_first_run[i+1]),
+ * each an external taxid (0 = minimizer not in the table) and the number of
+ * consecutive unambiguous k-mer positions that carry it — kraken2's `taxa`
+ * vector (classify.cc) without its ambiguous entries, which the host derives
+ * from the sequence itself.  Host pointers; *n_runs gets the total. */
+int nh_last_batch_runs(nh_session *s, uint64_t n_seqs, uint32_t *seq_first_run, uint32_t *run_taxon_ext,
+                       uint8_t *run_len, uint64_t run_capacity, uint64_t *n_runs);
 /* The CUDA stream (cudaStream_t) the session launches on. */
 void *nh_session_stream(nh_session *s);
 

@@ -47,6 +47,7 @@ class Params(C.Structure):
         ("confidence", C.c_double), ("minimum_hit_groups", C.c_int32), ("paired", C.c_int32),
         ("keep_human", C.c_int32), ("threads", C.c_int32),
         ("max_batch_bases", C.c_uint64), ("max_batch_seqs", C.c_uint64),
+        ("emit_runs", C.c_int32), ("reserved", C.c_int32),
     ]
 
 
@@ -101,6 +102,7 @@ SYMBOLS = {
     "nh_run_files_multi": (_i32, [C.POINTER(_vp), _i32, C.POINTER(Files), C.POINTER(RunStats)]),
     "nh_debug_rewrite_files": (_i32, [C.POINTER(Files), _vp, _vp, _u64, _i32, C.POINTER(RunStats)]),
     "nh_session_stream": (_vp, [_vp]),
+    "nh_last_batch_runs": (_i32, [_vp, _u64, _vp, _vp, _vp, _u64, C.POINTER(_u64)]),
     "nh_host_alloc": (_vp, [C.c_size_t]),
     "nh_host_free": (None, [_vp]),
     "nh_debug_minimizers": (_i32, [_vp, _vp, _vp, _u64, _vp, _vp, _vp]),

@@ -128,7 +128,7 @@ class Session:
 
     def __init__(self, db: Database, confidence: float = 0.0, paired: bool = False,
                  keep_human: bool = False, minimum_hit_groups: int = 2, threads: int = 1,
-                 max_batch_bases: int = 0, max_batch_seqs: int = 0):
+                 max_batch_bases: int = 0, max_batch_seqs: int = 0, emit_runs: bool = False):
         p = Params()
         p.confidence = float(confidence)
         p.minimum_hit_groups = int(minimum_hit_groups)
@@ -137,6 +137,7 @@ class Session:
         p.threads = int(threads)
         p.max_batch_bases = int(max_batch_bases)
         p.max_batch_seqs = int(max_batch_seqs)
+        p.emit_runs = int(emit_runs)
         self.paired = bool(paired)
         self.db = db
         self._h = C.c_void_p()
@@ -169,6 +170,16 @@ class Session:
                         d_out_call: int, d_out_keep: int) -> None:
         check(lib().nh_classify_batch_device(self._h, d_bases, d_offsets, n_seqs, total_bases,
                                              d_out_call, d_out_keep))
+
+    def last_batch_runs(self, n_seqs: int, capacity: int):
+        """(seq_first_run[n_seqs+1], run_taxon_ext, run_len) of the batch just classified."""
+        first = np.zeros(n_seqs + 1, np.uint32)
+        ext = np.zeros(max(capacity, 1), np.uint32)
+        ln = np.zeros(max(capacity, 1), np.uint8)
+        n = C.c_uint64()
+        check(lib().nh_last_batch_runs(self._h, n_seqs, first.ctypes.data, ext.ctypes.data, ln.ctypes.data,
+                                       capacity, C.byref(n)))
+        return first, ext[:n.value], ln[:n.value]
 
     def sync(self) -> BatchStats:
         st = BatchStats()

@@ -124,6 +124,10 @@ static int parse_opts_taxo(nh_db *db, const void *opts, size_t opts_len, const v
   db->h_parent.resize(node_count);
   db->h_ext.resize(node_count);
   db->h_ext64.resize(node_count);
+  db->h_name.assign(node_count, std::string());
+  db->h_rank.assign(node_count, std::string());
+  const uint64_t names_at = 32 + node_count * 56, ranks_at = names_at + name_len;
+  const bool have_strings = name_len < taxo_len && rank_len < taxo_len && ranks_at + rank_len <= taxo_len;
   for (uint64_t i = 0; i < node_count; i++) {
     uint64_t parent, ext;
     memcpy(&parent, tb + 32 + i * 56 + 0, 8);
@@ -138,6 +142,13 @@ static int parse_opts_taxo(nh_db *db, const void *opts, size_t opts_len, const v
     db->h_parent[i] = (uint32_t)parent;
     db->h_ext[i] = (uint32_t)ext;
     db->h_ext64[i] = ext;
+    if (have_strings && i > 0) {
+      uint64_t no, ro;
+      memcpy(&no, tb + 32 + i * 56 + 24, 8);
+      memcpy(&ro, tb + 32 + i * 56 + 32, 8);
+      if (no < name_len) db->h_name[i].assign((const char *)tb + names_at + no, strnlen((const char *)tb + names_at + no, name_len - no));
+      if (ro < rank_len) db->h_rank[i].assign((const char *)tb + ranks_at + ro, strnlen((const char *)tb + ranks_at + ro, rank_len - ro));
+    }
   }
   db->h_parent[0] = 0;
   return NH_OK;
@@ -395,6 +406,8 @@ extern "C" int nh_db_clone(const nh_db *src, int device, nh_db **out) {
   db->h_parent = src->h_parent;
   db->h_ext = src->h_ext;
   db->h_ext64 = src->h_ext64;
+  db->h_name = src->h_name;
+  db->h_rank = src->h_rank;
   const uint64_t cap = src->info.capacity;
   const size_t bytes = ((cap + 31) / 32) * 128;
   cudaError_t e = cudaMalloc(&db->d_cells, bytes);
@@ -503,6 +516,12 @@ extern "C" int nh_session_create(nh_db *db, const nh_params_t *params, nh_sessio
   ALLOC(s->d_overflow, ms);
   ALLOC(s->d_deferred, ms);
   ALLOC(s->d_counters, 1);
+  if (params->emit_runs) {
+    ALLOC(s->d_run_ext, s->cap_lookups);
+    ALLOC(s->d_run_len, s->cap_lookups);
+    ALLOC(s->d_tile_run_off, s->cap_tiles);
+    ALLOC(s->d_run_cursor, 1);
+  }
 #undef ALLOC
   if (e == cudaSuccess) e = cudaHostAlloc(&s->h_counters, sizeof(NhCounters), cudaHostAllocDefault);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
@@ -540,6 +559,10 @@ extern "C" void nh_session_destroy(nh_session *s) {
   cudaFree(s->d_overflow);
   cudaFree(s->d_deferred);
   cudaFree(s->d_counters);
+  cudaFree(s->d_run_ext);
+  cudaFree(s->d_run_len);
+  cudaFree(s->d_tile_run_off);
+  cudaFree(s->d_run_cursor);
   if (s->h_counters) cudaFreeHost(s->h_counters);
   for (int i = 0; i < NH_NUM_EVENTS; i++)
     if (s->ev[i]) cudaEventDestroy(s->ev[i]);
@@ -608,6 +631,7 @@ static int enqueue_batch(nh_session *s, const uint8_t *d_bases, const uint64_t *
   cudaEventRecord(s->ev[EV_PLAN0], st);
   const bool fused = s->use_fused;
   B.deferred_units = fused ? s->d_deferred : nullptr;
+  B.emit_all_taxa = s->params.emit_runs ? 1 : 0;
   launches += nh_launch_plan(P, B, st);
   cudaEventRecord(s->ev[EV_MIN0], st);
   if (fused) {
@@ -622,11 +646,15 @@ static int enqueue_batch(nh_session *s, const uint8_t *d_bases, const uint64_t *
   }
   cudaEventRecord(s->ev[EV_SCORE0], st);
   launches += nh_launch_score(P, B, SP, sm, st);
+  if (s->params.emit_runs)
+    launches += nh_launch_gather_runs(P, B, (uint32_t)tiles_upper, s->d_run_ext, s->d_run_len, s->d_tile_run_off,
+                                      s->d_run_cursor, sm, st);
   cudaEventRecord(s->ev[EV_SCORE1], st);
   cudaMemcpyAsync(s->h_counters, s->d_counters, sizeof(NhCounters), cudaMemcpyDeviceToHost, st);
   s->last_launches = (uint32_t)launches;
   s->last_fused = fused;
   s->last_units = B.n_units;
+  s->last_seqs = n_seqs;
   s->last_bases = total_bases;
   s->pending = true;
   cudaError_t e = cudaGetLastError();
@@ -797,6 +825,46 @@ extern "C" int nh_debug_last_batch(nh_session *s, uint32_t *out_call_internal,
     CUDA_TRY(cudaMemcpy(out_total_kmers, s->d_dbg_total, n_units * 4, cudaMemcpyDeviceToHost));
   if (out_hit_groups)
     CUDA_TRY(cudaMemcpy(out_hit_groups, s->d_dbg_groups, n_units * 4, cudaMemcpyDeviceToHost));
+  return NH_OK;
+}
+
+extern "C" int nh_last_batch_runs(nh_session *s, uint64_t n_seqs, uint32_t *seq_first_run,
+                                  uint32_t *run_taxon_ext, uint8_t *run_len, uint64_t run_capacity,
+                                  uint64_t *n_runs) {
+  if (!s || !seq_first_run || !run_taxon_ext || !run_len) return nh_set_error(NH_ERR_INVALID, "null argument");
+  if (!s->params.emit_runs) return nh_set_error(NH_ERR_INVALID, "session was not created with emit_runs");
+  if (n_seqs != s->last_seqs) return nh_set_error(NH_ERR_INVALID, "last batch had %llu sequences", (unsigned long long)s->last_seqs);
+  CUDA_TRY(cudaSetDevice(s->db->info.device));
+  CUDA_TRY(cudaStreamSynchronize(s->stream));
+  const uint32_t n_tiles = s->h_counters->n_tiles;
+  uint32_t total = 0;
+  CUDA_TRY(cudaMemcpy(&total, s->d_run_cursor, 4, cudaMemcpyDeviceToHost));
+  if (n_runs) *n_runs = total;
+  if (total > run_capacity) return nh_set_error(NH_ERR_CAPACITY, "%u runs do not fit the caller's %llu", total, (unsigned long long)run_capacity);
+  std::vector<uint32_t> tile_base(n_seqs + 1), tile_off(n_tiles), ext(total);
+  std::vector<NhTileOut> tile_out(n_tiles);
+  std::vector<uint8_t> len(total);
+  CUDA_TRY(cudaMemcpy(tile_base.data(), s->d_tile_base, (n_seqs + 1) * 4, cudaMemcpyDeviceToHost));
+  if (n_tiles) {
+    CUDA_TRY(cudaMemcpy(tile_off.data(), s->d_tile_run_off, (size_t)n_tiles * 4, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(tile_out.data(), s->d_tile_out, (size_t)n_tiles * sizeof(NhTileOut), cudaMemcpyDeviceToHost));
+  }
+  if (total) {
+    CUDA_TRY(cudaMemcpy(ext.data(), s->d_run_ext, (size_t)total * 4, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(len.data(), s->d_run_len, total, cudaMemcpyDeviceToHost));
+  }
+  /* tiles were packed in completion order; hand the runs back in sequence order */
+  uint32_t o = 0;
+  for (uint64_t i = 0; i < n_seqs; i++) {
+    seq_first_run[i] = o;
+    for (uint32_t t = tile_base[i]; t < tile_base[i + 1]; t++) {
+      const uint32_t n = tile_out[t].lk_cnt, from = tile_off[t];
+      memcpy(run_taxon_ext + o, ext.data() + from, (size_t)n * 4);
+      memcpy(run_len + o, len.data() + from, n);
+      o += n;
+    }
+  }
+  seq_first_run[n_seqs] = o;
   return NH_OK;
 }
 

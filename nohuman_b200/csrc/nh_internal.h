@@ -31,6 +31,7 @@ struct nh_db {
   uint32_t *d_ext = nullptr;
   std::vector<uint32_t> h_parent, h_ext;
   std::vector<uint64_t> h_ext64;
+  std::vector<std::string> h_name, h_rank; /* taxo.k2d name / rank strings per node (reports) */
   int sm_count = 0;
 };
 
@@ -53,6 +54,9 @@ struct nh_session {
   uint32_t *d_dbg_call = nullptr, *d_dbg_total = nullptr, *d_dbg_groups = nullptr;
   uint32_t *d_overflow = nullptr;
   uint32_t *d_deferred = nullptr;
+  uint32_t *d_run_ext = nullptr, *d_tile_run_off = nullptr, *d_run_cursor = nullptr;
+  uint8_t *d_run_len = nullptr;
+  uint64_t last_seqs = 0;
   bool use_fused = false, last_fused = false;
   int lane_taxa = NH_LANE_TAXA;
   NhCounters *d_counters = nullptr;

@@ -938,9 +938,8 @@ k_scan_probe_score(const NhDbParams db, const NhBatchPtrs b, const NhScoreParams
       qn = __popc(cmask);
       if (leader && done) {
         const uint32_t mt = sm.meta[aux & 31u];
-        if (mt & NH_META_DEFERRED) {
-          b.lk_taxon[oslot] = result;
-        } else if (result) {
+        if ((mt & NH_META_DEFERRED) || b.emit_all_taxa) b.lk_taxon[oslot] = result;
+        if (!(mt & NH_META_DEFERRED) && result) {
           const uint32_t own = mt;
           const uint32_t n = (uint32_t)__ldcg(b.lk_cnt + oslot);
           atomicAdd(&sm.groups[own], 1u);
@@ -1022,6 +1021,29 @@ k_scan_probe_score(const NhDbParams db, const NhBatchPtrs b, const NhScoreParams
     if (tot_lookups) atomicAdd(&b.counters->n_lookups, tot_lookups);
     if (tot_classified) atomicAdd(&b.counters->n_classified, tot_classified);
     if (tot_kept) atomicAdd(&b.counters->n_kept, tot_kept);
+  }
+}
+
+/* ------------------------------------------------------------------ */
+/* per-read output support: pack every tile's (external taxid, run length) */
+
+__global__ void __launch_bounds__(NH_BLOCK_THREADS)
+k_gather_runs(const NhDbParams db, const NhBatchPtrs b, uint32_t *__restrict__ run_ext,
+              uint8_t *__restrict__ run_len, uint32_t *__restrict__ tile_run_off,
+              uint32_t *__restrict__ cursor) {
+  const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+  const uint32_t n_tiles = b.counters->n_tiles;
+  for (uint32_t tile = blockIdx.x * NH_WARPS_PER_BLOCK + warp; tile < n_tiles;
+       tile += gridDim.x * NH_WARPS_PER_BLOCK) {
+    const NhTileOut to = b.tile_out[tile];
+    uint32_t base = 0;
+    if (lane == 0) base = to.lk_cnt ? atomicAdd(cursor, to.lk_cnt) : 0u;
+    base = __shfl_sync(FULL_MASK, base, 0);
+    if (lane == 0) tile_run_off[tile] = base;
+    for (uint32_t j = lane; j < to.lk_cnt; j += 32u) {
+      run_ext[base + j] = db.ext_id[b.lk_taxon[to.lk_off + j]];
+      run_len[base + j] = b.lk_cnt[to.lk_off + j];
+    }
   }
 }
 
@@ -1147,6 +1169,18 @@ int nh_launch_score(const NhDbParams &db, const NhBatchPtrs &b, const NhScorePar
     k_score<false><<<grid, NH_BLOCK_THREADS, hash_bytes, st>>>(db, b, sp);
   k_score_big<<<sm_count, 32, NH_BIG_HASH_SLOTS * 8, st>>>(db, b, sp);
   return 2;
+}
+
+int nh_launch_gather_runs(const NhDbParams &db, const NhBatchPtrs &b, uint32_t tiles_upper,
+                          uint32_t *run_ext, uint8_t *run_len, uint32_t *tile_run_off,
+                          uint32_t *cursor, int sm_count, cudaStream_t st) {
+  uint32_t blocks = (tiles_upper + NH_WARPS_PER_BLOCK - 1) / NH_WARPS_PER_BLOCK;
+  uint32_t max_grid = (uint32_t)sm_count * 8u;
+  uint32_t grid = blocks < max_grid ? blocks : max_grid;
+  if (grid == 0) grid = 1;
+  cudaMemsetAsync(cursor, 0, 4, st);
+  k_gather_runs<<<grid, NH_BLOCK_THREADS, 0, st>>>(db, b, run_ext, run_len, tile_run_off, cursor);
+  return 1;
 }
 
 int nh_launch_random_gather(const uint32_t *cells, uint64_t n_sectors, uint64_t n_reads,

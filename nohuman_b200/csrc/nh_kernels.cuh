@@ -95,6 +95,7 @@ struct NhBatchPtrs {
   uint32_t *dbg_hit_groups;
   uint32_t *overflow_units;
   uint32_t *deferred_units; /* null: k_score walks every unit (legacy path) */
+  int32_t emit_all_taxa;    /* fused kernel: store lk_taxon for every tile (per-read output wanted) */
   NhCounters *counters;
   /* per-position debug output of the minimizer kernel (may be null) */
   const uint64_t *dbg_pos_offsets;
@@ -121,6 +122,10 @@ int nh_launch_probe(const NhDbParams &db, const uint64_t *keys, uint32_t *taxa,
                     const uint32_t *n_dev, uint32_t n_upper, int sm_count, cudaStream_t st);
 int nh_launch_score(const NhDbParams &db, const NhBatchPtrs &b, const NhScoreParams &sp,
                     int sm_count, cudaStream_t st);
+/* per-tile runs (external taxid, k-mer count) packed densely for the per-read kraken output */
+int nh_launch_gather_runs(const NhDbParams &db, const NhBatchPtrs &b, uint32_t tiles_upper,
+                          uint32_t *run_ext, uint8_t *run_len, uint32_t *tile_run_off,
+                          uint32_t *cursor, int sm_count, cudaStream_t st);
 int nh_launch_random_gather(const uint32_t *cells, uint64_t n_sectors, uint64_t n_reads,
                             uint64_t seed, uint32_t *sink, int sm_count, cudaStream_t st);
 cudaError_t nh_kernels_init(void);

@@ -6,13 +6,19 @@
  *
  *   reader thread per input file   inflate (zlib; bzip2 through a pipe) + FASTQ/FASTA parse
  *        |  chunks of NH_CHUNK_RECORDS records
- *   classifier threads (2)         mates interleaved into PINNED bases/offsets,
+ *   classifier threads (2 per GPU) mates interleaved into PINNED bases/offsets,
  *        |                         nh_classify_batch (H2D, kernels, D2H) on their own session
  *   writer thread                  batches back in input order, kept records re-serialised
  *        |                         the way kraken2 prints them, cut into blocks
  *   compressor pool (-t threads)   every block an independent gzip member / zstd frame
  *        |                         (what gzp does for the reference), written in order
  *   final out1 / out2              no temporary FASTQ, no second pass
+ *
+ * With --kraken-output the sessions keep per-sequence hit runs
+ * (nh_last_batch_runs) and the writer prints kraken2's per-read line
+ * "C|U <id> <taxid> <len[|len2]> <hitlist>" (classify.cc, AddHitlistString);
+ * with --kraken-report it prints the clade-aggregated report at the end
+ * (reports.cc ReportKrakenStyle / KrakenReportDFS).
  *
  * What kraken2 does on this path and is restated here (upstream seqreader.cc /
  * classify.cc): format auto-detected from the first byte ('@'
@@ -36,8 +42,10 @@
 #include <chrono>
 #include <condition_variable>
 #include <deque>
+#include <algorithm>
 #include <map>
 #include <memory>
+#include <unordered_map>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -563,6 +571,8 @@ struct Work {
   uint64_t n_units = 0;
   std::vector<uint32_t> call;
   std::vector<uint8_t> keep;
+  std::vector<uint32_t> first_run, run_ext; /* per-sequence hit runs (kraken output only) */
+  std::vector<uint8_t> run_len;
   std::string error;
 };
 
@@ -592,14 +602,166 @@ static void append_record(std::string &out, const Chunk &c, const Rec &r, bool t
   }
 }
 
+static inline bool is_acgt(unsigned char c) {
+  c &= 0xDF;
+  return c == 'A' || c == 'C' || c == 'G' || c == 'T';
+}
+
+/* run-length printer of kraken2's `taxa` vector (classify.cc AddHitlistString) */
+struct Hitlist {
+  static constexpr int64_t NONE = -1, AMBIG = -2, BORDER = -3;
+  std::string &out;
+  int64_t last = NONE;
+  uint64_t count = 0;
+  bool any = false;
+  explicit Hitlist(std::string &o) : out(o) {}
+  void flush() {
+    if (last == NONE) return;
+    if (any) out.push_back(' ');
+    any = true;
+    char buf[48];
+    int n;
+    if (last == BORDER)
+      n = snprintf(buf, sizeof buf, "|:|");
+    else if (last == AMBIG)
+      n = snprintf(buf, sizeof buf, "A:%llu", (unsigned long long)count);
+    else
+      n = snprintf(buf, sizeof buf, "%lld:%llu", (long long)last, (unsigned long long)count);
+    out.append(buf, (size_t)n);
+  }
+  void push(int64_t code) {
+    if (code == last) {
+      count++;
+      return;
+    }
+    flush();
+    last = code;
+    count = 1;
+  }
+  void finish() {
+    flush();
+    if (!any) out.append("0:0");
+  }
+};
+
+/* one line of kraken2's --output for unit i of w */
+static void append_kraken_line(std::string &out, const Work &w, uint64_t i, int nf, int k, int amb_span) {
+  out.push_back(w.call[i] ? 'C' : 'U');
+  out.push_back('\t');
+  {
+    const Rec &r = w.c[0].recs[i];
+    const char *h = w.c[0].text.data() + r.hdr_off + 1;
+    size_t n = 0;
+    while (n + 1 < r.hdr_len && !isspace((unsigned char)h[n])) n++;
+    if (nf == 2 && n > 2 && h[n - 2] == '/' && (h[n - 1] == '1' || h[n - 1] == '2')) n -= 2; /* TrimPairInfo */
+    out.append(h, n);
+  }
+  char buf[64];
+  int n = snprintf(buf, sizeof buf, "\t%u\t", w.call[i]);
+  out.append(buf, (size_t)n);
+  for (int f = 0; f < nf; f++) {
+    n = snprintf(buf, sizeof buf, f ? "|%u" : "%u", w.c[f].recs[i].seq_len);
+    out.append(buf, (size_t)n);
+  }
+  out.push_back('\t');
+  Hitlist hl(out);
+  for (int f = 0; f < nf; f++) {
+    const Rec &r = w.c[f].recs[i];
+    const unsigned char *s = (const unsigned char *)w.c[f].text.data() + r.seq_off;
+    const uint64_t seq = i * nf + f;
+    uint32_t ri = w.first_run[seq];
+    const uint32_t rend = w.first_run[seq + 1];
+    uint32_t left = ri < rend ? w.run_len[ri] : 0;
+    uint32_t c_run = 0;
+    for (uint32_t b = 0; b < r.seq_len; b++) {
+      c_run = is_acgt(s[b]) ? c_run + 1 : 0;
+      if (b + 1 < (uint32_t)k) continue;
+      if (c_run >= (uint32_t)amb_span && ri < rend) {
+        hl.push((int64_t)w.run_ext[ri]);
+        if (--left == 0 && ++ri < rend) left = w.run_len[ri];
+      } else {
+        hl.push(Hitlist::AMBIG);
+      }
+    }
+    if (nf == 2 && f == 0) hl.push(Hitlist::BORDER);
+  }
+  hl.finish();
+  out.push_back('\n');
+}
+
+/* kraken2 report (reports.cc ReportKrakenStyle): percentage, clade count, direct count, rank code, taxid, indented name */
+static bool write_report(const char *path, const nh_db *db, const std::vector<uint64_t> &call_counts, uint64_t total,
+                         uint64_t unclassified) {
+  FILE *f = fopen(path, "w");
+  if (!f) return false;
+  const size_t n = db->h_parent.size();
+  std::vector<uint64_t> clade(call_counts);
+  for (size_t i = n - 1; i >= 2; i--) clade[db->h_parent[i]] += clade[i]; /* parent id < child id */
+  std::vector<std::vector<uint32_t>> kids(n);
+  for (size_t i = 2; i < n; i++) kids[db->h_parent[i]].push_back((uint32_t)i);
+  auto line = [&](uint64_t cl, uint64_t direct, const std::string &rank, uint64_t taxid, const std::string &name, int depth) {
+    fprintf(f, "%6.2f\t%llu\t%llu\t%s\t%llu\t%*s%s\n", total ? 100.0 * (double)cl / (double)total : 0.0,
+            (unsigned long long)cl, (unsigned long long)direct, rank.c_str(), (unsigned long long)taxid, 2 * depth, "",
+            name.c_str());
+  };
+  if (unclassified) line(unclassified, unclassified, "U", 0, "unclassified", 0);
+  struct Frame {
+    uint32_t id;
+    char code;
+    int rank_depth, depth;
+  };
+  std::vector<Frame> stack;
+  if (n > 1) stack.push_back({1, 'R', -1, 0});
+  while (!stack.empty()) {
+    Frame fr = stack.back();
+    stack.pop_back();
+    if (clade[fr.id] == 0) continue;
+    const std::string &rank = db->h_rank[fr.id];
+    static const std::pair<const char *, char> codes[] = {{"superkingdom", 'D'}, {"kingdom", 'K'}, {"phylum", 'P'}, {"class", 'C'},
+                                                          {"order", 'O'},        {"family", 'F'},  {"genus", 'G'},  {"species", 'S'}};
+    bool named = false;
+    for (auto &c : codes)
+      if (rank == c.first) {
+        fr.code = c.second;
+        fr.rank_depth = 0;
+        named = true;
+      }
+    if (!named) fr.rank_depth++;
+    std::string rs(1, fr.code);
+    if (fr.rank_depth != 0) rs += std::to_string(fr.rank_depth);
+    line(clade[fr.id], call_counts[fr.id], rs, db->h_ext64[fr.id], db->h_name[fr.id], fr.depth);
+    std::vector<uint32_t> ch = kids[fr.id];
+    std::stable_sort(ch.begin(), ch.end(), [&](uint32_t a, uint32_t b) { return clade[a] > clade[b]; });
+    for (auto it = ch.rbegin(); it != ch.rend(); ++it) stack.push_back({*it, fr.code, fr.rank_depth, fr.depth + 1});
+  }
+  return fclose(f) == 0;
+}
+
 static int run_pipeline(const Decider &dec, const nh_files_t *files, nh_run_stats_t *stats) {
   const auto t0 = std::chrono::steady_clock::now();
   const bool paired = files->in2 != nullptr;
   const int nf = paired ? 2 : 1;
   if (!files->in1 || !files->out1 || (paired && !files->out2))
     return nh_set_error(NH_ERR_INVALID, "nh_run_files: in1/out1 (and out2 for paired input) are required");
-  if ((files->kraken_output && strcmp(files->kraken_output, "/dev/null") != 0) || files->kraken_report)
-    return nh_set_error(NH_ERR_UNSUPPORTED, "--kraken-output / --kraken-report are not produced by this build");
+  const bool want_lines = files->kraken_output && strcmp(files->kraken_output, "/dev/null") != 0;
+  const bool want_report = files->kraken_report != nullptr;
+  if ((want_lines || want_report) && dec.dbs.empty())
+    return nh_set_error(NH_ERR_UNSUPPORTED, "kraken output / report need the database (not available to the rewrite hook)");
+  FILE *kout = nullptr;
+  if (want_lines) {
+    kout = fopen(files->kraken_output, "w");
+    if (!kout) return nh_set_error(NH_ERR_IO, "cannot create %s", files->kraken_output);
+    setvbuf(kout, nullptr, _IOFBF, 1u << 20);
+  }
+  std::unordered_map<uint32_t, uint32_t> ext_to_internal;
+  std::vector<uint64_t> call_counts;
+  if (want_report) {
+    const nh_db *d0 = dec.dbs[0];
+    call_counts.assign(d0->h_ext.size(), 0);
+    for (size_t i = 1; i < d0->h_ext.size(); i++) ext_to_internal[d0->h_ext[i]] = (uint32_t)i;
+  }
+  const int db_k = dec.dbs.empty() ? 0 : (int)dec.dbs[0]->info.k;
+  const int db_amb_span = dec.dbs.empty() ? 0 : dec.dbs[0]->params.amb_span;
   int fmt = files->out_format ? files->out_format : 'u';
   if (!strchr("ugbxz", fmt)) return nh_set_error(NH_ERR_INVALID, "unknown output format '%c'", fmt);
   const int threads = dec.params.threads < 1 ? 1 : dec.params.threads;
@@ -708,6 +870,7 @@ static int run_pipeline(const Decider &dec, const nh_files_t *files, nh_run_stat
               nh_params_t p = dec.params;
               p.max_batch_bases = cap_bases;
               p.max_batch_seqs = cap_seqs;
+              p.emit_runs = want_lines ? 1 : 0;
               h_bases = (uint8_t *)nh_host_alloc(cap_bases);
               h_off = (uint64_t *)nh_host_alloc(cap_seqs * 8);
               if (!h_bases || !h_off || nh_session_create(dec.dbs[(size_t)ci % dec.dbs.size()], &p, &sess) != NH_OK) {
@@ -727,6 +890,14 @@ static int run_pipeline(const Decider &dec, const nh_files_t *files, nh_run_stat
               h_off[s] = o;
               if (nh_classify_batch(sess, h_bases, h_off, n_seqs, w->call.data(), w->keep.data(), nullptr) != NH_OK)
                 w->error = std::string("classification failed: ") + nh_last_error();
+              if (want_lines && w->error.empty()) {
+                w->first_run.resize(n_seqs + 1);
+                w->run_ext.resize(total + 1);
+                w->run_len.resize(total + 1);
+                uint64_t nr = 0;
+                if (nh_last_batch_runs(sess, n_seqs, w->first_run.data(), w->run_ext.data(), w->run_len.data(), total + 1, &nr) != NH_OK)
+                  w->error = std::string("reading the hit runs failed: ") + nh_last_error();
+              }
             }
           }
         }
@@ -762,6 +933,18 @@ static int run_pipeline(const Decider &dec, const nh_files_t *files, nh_run_stat
       failed = true;
     }
     if (failed) continue; /* drain */
+    if (kout) {
+      std::string lines;
+      lines.reserve(w->n_units * 96);
+      for (uint64_t i = 0; i < w->n_units; i++) append_kraken_line(lines, *w, i, nf, db_k, db_amb_span);
+      if (fwrite(lines.data(), 1, lines.size(), kout) != lines.size()) {
+        failed = true;
+        fail_msg = std::string("writing ") + files->kraken_output + " failed";
+      }
+    }
+    if (want_report)
+      for (uint64_t i = 0; i < w->n_units; i++)
+        if (w->call[i]) call_counts[ext_to_internal[w->call[i]]]++;
     for (uint64_t i = 0; i < w->n_units; i++) {
       const bool classified = w->call[i] != 0;
       n_classified += classified;
@@ -785,6 +968,15 @@ static int run_pipeline(const Decider &dec, const nh_files_t *files, nh_run_stat
   bool wrote = bw.finish();
   for (int f = 0; f < nf; f++) wrote = outs[f].close() && wrote;
   (void)keep_human;
+  if (kout && fclose(kout) != 0 && !failed) {
+    failed = true;
+    fail_msg = std::string("writing ") + files->kraken_output + " failed";
+  }
+  if (want_report && !failed &&
+      !write_report(files->kraken_report, dec.dbs[0], call_counts, total_units, total_units - n_classified)) {
+    failed = true;
+    fail_msg = std::string("writing ") + files->kraken_report + " failed";
+  }
   if (failed) return nh_set_error(NH_ERR_IO, "%s", fail_msg.c_str());
   if (!wrote) return nh_set_error(NH_ERR_IO, "writing %s failed", outs[0].path().c_str());
   if (stats) {

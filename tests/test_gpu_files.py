@@ -168,3 +168,125 @@ def test_replicated_database_and_sharded_batches(small_db, gpu_db, reads, tmp_pa
                         reads["paths"]["m1"], reads["paths"]["m2"]], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     assert open(str(tmp_path / "c1.fq"), "rb").read() == expected_fastq(reads["m1"], "p", "/1", ext == 0, np.zeros_like(ext))
+
+
+def kraken_line(db, name, seqs, paired):
+    r = db.classify_one(bytes(seqs[0]), bytes(seqs[1]) if paired else None, want_taxa=True)
+    if paired and len(name) > 2 and name[-2] == "/" and name[-1] in "12":
+        name = name[:-2]
+    lens = "|".join(str(len(s)) for s in seqs)
+    return f"{'C' if r['call'] else 'U'}\t{name}\t{r['ext_call']}\t{lens}\t{r['hitlist']}\n", r["call"]
+
+
+def py_report(db, calls_internal, total):
+    """kraken2 reports.cc ReportKrakenStyle restated (recalled upstream behaviour, see module docstring of the product)"""
+    par = db.parents().tolist()
+    ext = db.external_ids().tolist()
+    n = len(par)
+    import ctypes as C
+    names = [C.string_at(db.tax.name_data + db.tax.nodes[i].name_offset).decode() if i else "" for i in range(n)]
+    ranks = [C.string_at(db.tax.rank_data + db.tax.nodes[i].rank_offset).decode() if i else "" for i in range(n)]
+    direct = [0] * n
+    for c in calls_internal:
+        if c:
+            direct[c] += 1
+    clade = list(direct)
+    for i in range(n - 1, 1, -1):
+        clade[par[i]] += clade[i]
+    kids = [[] for _ in range(n)]
+    for i in range(2, n):
+        kids[par[i]].append(i)
+    out = []
+    uncls = total - sum(direct)
+    fmt = lambda cl, d, rk, tid, name, depth: "%6.2f\t%d\t%d\t%s\t%d\t%s%s\n" % (100.0 * cl / total, cl, d, rk, tid, "  " * depth, name)
+    if uncls:
+        out.append(fmt(uncls, uncls, "U", 0, "unclassified", 0))
+    codes = {"superkingdom": "D", "kingdom": "K", "phylum": "P", "class": "C", "order": "O", "family": "F", "genus": "G", "species": "S"}
+
+    def dfs(t, code, rdepth, depth):
+        if clade[t] == 0:
+            return
+        if ranks[t] in codes:
+            code, rdepth = codes[ranks[t]], 0
+        else:
+            rdepth += 1
+        out.append(fmt(clade[t], direct[t], code + (str(rdepth) if rdepth else ""), ext[t], names[t], depth))
+        for c in sorted(kids[t], key=lambda x: -clade[x]):
+            dfs(c, code, rdepth, depth + 1)
+    dfs(1, "R", -1, 0)
+    return "".join(out)
+
+
+@pytest.mark.parametrize("paired", [False, True])
+def test_kraken_output_lines_and_report(small_db, gpu_db, reads, tmp_path, paired):
+    """--kraken-output (per-read lines with the run-length hitlist) and --kraken-report, rows (f)-2/3 of SURVEY §8"""
+    from nohuman_b200 import Session
+    from nohuman_b200.api import make_files
+    from nohuman_b200._ffi import RunStats, check, lib
+    import ctypes as C
+    small_db.confidence = 0.1
+    if paired:
+        m1, m2 = reads["m1"][:600], reads["m2"][:600]
+        # ragged cases: a mate shorter than k, a mate with N runs
+        m1 = m1 + [reads["m1"][0][:20], reads["m1"][1]]
+        bad = reads["m2"][1].copy(); bad[40:45] = ord("N"); bad[100] = ord("n")
+        m2 = m2 + [reads["m2"][0], bad]
+        p1, p2 = str(tmp_path / "k_1.fq"), str(tmp_path / "k_2.fq")
+        open(p1, "wb").write(fastq_bytes(m1, "q", "/1"))
+        open(p2, "wb").write(fastq_bytes(m2, "q", "/2"))
+        units = [(f"q{i}/1", (m1[i], m2[i])) for i in range(len(m1))]
+    else:
+        se = reads["se"][:800] + synth.ont_reads(small_db.genomes, 6, seed=9, n50=1500, max_len=5000)
+        p1, p2 = str(tmp_path / "k.fq"), None
+        open(p1, "wb").write(fastq_bytes(se, "q"))
+        units = [(f"q{i}", (se[i],)) for i in range(len(se))]
+    want_lines, calls = [], []
+    for name, seqs in units:
+        line, call = kraken_line(small_db, name, seqs, paired)
+        want_lines.append(line)
+        calls.append(call)
+    kout, krep = str(tmp_path / "kraken.out"), str(tmp_path / "kraken.report")
+    f = make_files(p1, str(tmp_path / "o1.fq"), p2, str(tmp_path / "o2.fq") if paired else None)
+    f.kraken_output, f.kraken_report = kout.encode(), krep.encode()
+    st = RunStats()
+    with Session(gpu_db, confidence=0.1, paired=paired, threads=2) as sess:
+        check(lib().nh_run_files(sess._h, C.byref(f), C.byref(st)))
+    got = open(kout).read().splitlines(keepends=True)
+    assert len(got) == len(want_lines)
+    for g, w in zip(got, want_lines):
+        assert g == w
+    assert any(" A:" in l for l in got) and (not paired or all("|:|" in l for l in got))
+    assert open(krep).read() == py_report(small_db, calls, len(units))
+    rep = open(krep).read().splitlines()
+    assert rep[0].split("\t")[3] == "U" and any(l.split("\t")[3] == "S" and l.endswith("Homo sapiens") for l in rep)
+    small_db.confidence = 0.0
+
+
+def test_last_batch_runs_match_oracle_taxa(small_db, gpu_db):
+    from nohuman_b200 import Session
+    seqs = synth.illumina_reads(small_db.genomes, 200, 150, seed=51, n_rate=0.3)
+    seqs += synth.ont_reads(small_db.genomes, 5, seed=52, n50=2000, max_len=6000)
+    bases, offsets = synth.pack(seqs)
+    with Session(gpu_db, emit_runs=True) as sess:
+        sess.classify(bases, offsets)
+        first, ext, ln = sess.last_batch_runs(len(seqs), int(offsets[-1]))
+    ext_ids = small_db.external_ids()
+    for i, s in enumerate(seqs):
+        taxa = small_db.classify_one(bytes(s), want_taxa=True)["taxa"]
+        # oracle positions without the ambiguous ones, run-length encoded on the external id
+        want = []
+        for t in taxa:
+            if t >= (1 << 64) - 3:
+                continue
+            e = int(ext_ids[t])
+            if want and want[-1][0] == e:
+                want[-1][1] += 1
+            else:
+                want.append([e, 1])
+        got = []
+        for j in range(int(first[i]), int(first[i + 1])):
+            if got and got[-1][0] == int(ext[j]):
+                got[-1][1] += int(ln[j])
+            else:
+                got.append([int(ext[j]), int(ln[j])])
+        assert got == want, i
