@@ -490,9 +490,19 @@ extern "C" int nh_session_create(nh_db *db, const nh_params_t *params, nh_sessio
     int v = lt ? atoi(lt) : NH_LANE_TAXA;
     s->lane_taxa = v < 1 ? 1 : (v > NH_LANE_TAXA ? NH_LANE_TAXA : v);
   }
-  const NhDbParams &P = db->params;
-  /* every sequence has at most ceil(positions / tile_pos) tiles */
-  s->cap_tiles = ms + mb / (uint64_t)P.tile_pos + 1;
+  /* The session works on its own copy of the constants: the lane-serial fused kernel takes
+   * tiles of up to NH_FUSED_TILE_POS k-mer positions (u8 run lengths cap them at 255); longer
+   * tiles make 250 bp reads single-tile units and halve the (k-1)-base overlap long reads pay. */
+  s->P = db->params;
+  if (s->use_fused) {
+    const char *tp = getenv("NH_FUSED_TILE_POS");
+    int v = tp ? atoi(tp) : NH_FUSED_TILE_POS;
+    s->P.tile_pos = v < 16 ? 16 : (v > 255 ? 255 : v);
+  }
+  const NhDbParams &P = s->P;
+  /* every sequence has at most ceil(positions / tile_pos) tiles; sized for the smaller
+   * (warp-per-tile) tiles, which the synthetic builder uses on this session's buffers */
+  s->cap_tiles = ms + mb / (uint64_t)(P.tile_pos < db->params.tile_pos ? P.tile_pos : db->params.tile_pos) + 1;
   /* one lookup per k-mer position at most */
   s->cap_lookups = mb;
   cudaError_t e = cudaSuccess;
@@ -591,7 +601,7 @@ static int enqueue_batch(nh_session *s, const uint8_t *d_bases, const uint64_t *
                          uint64_t n_seqs, uint64_t total_bases, uint32_t *d_out_call,
                          uint8_t *d_out_keep, bool with_debug, const uint64_t *d_pos_off,
                          uint64_t *d_pos_min, uint8_t *d_pos_amb) {
-  const NhDbParams &P = s->db->params;
+  const NhDbParams &P = s->P;
   NhBatchPtrs B;
   memset(&B, 0, sizeof B);
   B.bases = d_bases;

@@ -37,6 +37,7 @@ struct nh_db {
 
 struct nh_session {
   nh_db *db = nullptr;
+  NhDbParams P{}; /* db->params with this session's tile size */
   nh_params_t params{};
   uint64_t cap_bases = 0, cap_seqs = 0, cap_tiles = 0, cap_lookups = 0;
   size_t device_bytes = 0;

@@ -12,7 +12,8 @@
 
 #define NH_WARPS_PER_BLOCK 8
 #define NH_BLOCK_THREADS (NH_WARPS_PER_BLOCK * 32)
-#define NH_TILE_LMERS 128           /* l-mers per minimizer tile (4 warp iterations) */
+#define NH_TILE_LMERS 128           /* l-mers per minimizer tile of the warp-per-tile kernel (4 warp iterations) */
+#define NH_FUSED_TILE_POS 252       /* k-mer positions per tile of the lane-serial fused kernel (<= 255) */
 #define NH_MAX_WINDOW 32            /* k - l + 1 must fit one warp */
 #define NH_SMEM_PARENT_MAX 8192     /* taxonomy nodes staged in shared memory */
 #define NH_WARP_HASH_SLOTS 64       /* per-read taxon->count table (fast path) */

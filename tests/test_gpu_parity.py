@@ -118,7 +118,7 @@ def test_edge_cases(small_db, gpu_db):
         _compare_batch(small_db, sess, pseqs, True, 0.2)
 
 
-@pytest.mark.parametrize("mode", ["legacy", "lane_taxa_1", "lane_taxa_2"])
+@pytest.mark.parametrize("mode", ["legacy", "lane_taxa_1", "lane_taxa_2", "tile_pos_60", "probe_lanes_2", "probe_lanes_4"])
 def test_kernel_path_variants_match_oracle(small_db, gpu_db, mode, monkeypatch):
     """The warp-per-tile kernels (NH_LEGACY_KERNELS=1) and the fused kernel with a
     shrunken in-warp taxon table (units overflow into k_score_big, which probes
@@ -126,6 +126,10 @@ def test_kernel_path_variants_match_oracle(small_db, gpu_db, mode, monkeypatch):
     from nohuman_b200 import Session
     if mode == "legacy":
         monkeypatch.setenv("NH_LEGACY_KERNELS", "1")
+    elif mode.startswith("tile_pos"):
+        monkeypatch.setenv("NH_FUSED_TILE_POS", mode.split("_")[-1])  # every 150 bp read becomes a multi-tile unit
+    elif mode.startswith("probe_lanes"):
+        pytest.skip("NH_PROBE_LANES is read once per process; covered by running the suite with it set")
     else:
         monkeypatch.setenv("NH_TEST_LANE_TAXA", mode[-1])
     g = dict(small_db.genomes)

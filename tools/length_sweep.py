@@ -57,7 +57,7 @@ def main():
                      "classified_frac": round(st.n_classified / n, 4)})
         print(json.dumps(rows[-1]), file=sys.stderr)
         del d_bases, d_off
-    print(json.dumps({"workload": "read-length sweep, single-end, 50% genome-derived, keep-human, synthetic 2^%d-cell table" % args.capacity_log2,
+    print(json.dumps({"workload": "read-length sweep, single-end, 50%% genome-derived, keep-human, synthetic 2^%d-cell table" % args.capacity_log2,
                       "rows": rows}, indent=1))
 
 
