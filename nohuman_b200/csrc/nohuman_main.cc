@@ -283,6 +283,8 @@ static int kraken2_shim(int argc, char **argv) {
   p.paired = paired;
   p.keep_human = !cls_out.empty();
   p.threads = threads;
+  p.max_batch_bases = 1u << 20; /* parameter carrier only: nh_run_files sizes its own sessions per chunk */
+  p.max_batch_seqs = 1u << 12;
   nh_files_t f;
   memset(&f, 0, sizeof f);
   f.in1 = in[0].c_str();
@@ -464,6 +466,8 @@ int main(int argc, char **argv) {
   p.paired = paired;
   p.keep_human = human;
   p.threads = (int)threads;
+  p.max_batch_bases = 1u << 20; /* parameter carrier only: nh_run_files sizes its own sessions per chunk */
+  p.max_batch_seqs = 1u << 12;
   nh_session *sess = nullptr;
   if (nh_session_create(dbh, &p, &sess)) return fail("%s", nh_last_error());
   /* more GPUs: replicate the table once (peer copies), no exchange afterwards */

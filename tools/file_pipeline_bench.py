@@ -71,12 +71,14 @@ def main():
                             ("gzip in, plain out", p1 + ".gz", p2 + ".gz", "u")):
         o1, o2 = os.path.join(d, "o1"), os.path.join(d, "o2")
         t0 = time.perf_counter()
-        r = subprocess.run([cli, "--db", db_dir, "-t", str(args.threads), "--conf", "0.5", "-F", fmt, "-o", o1, "-O", o2, a, b],
+        r = subprocess.run([cli, "-v", "--db", db_dir, "-t", str(args.threads), "--conf", "0.5", "-F", fmt, "-o", o1, "-O", o2, a, b],
                            capture_output=True, text=True)
         dt = time.perf_counter() - t0
         assert r.returncode == 0, r.stderr
         line = [l for l in r.stderr.splitlines() if "classified as human" in l][0].split("] ", 1)[1]
+        pipe_s = float([l for l in r.stderr.splitlines() if "DEBUG" in l and " s, " in l][0].split("] ", 1)[1].split(" s")[0])
         rows.append({"variant": name, "seconds": round(dt, 2), "gbp_s": round(gbp / dt, 3),
+                     "pipeline_seconds": pipe_s, "pipeline_gbp_s": round(gbp / pipe_s, 3),
                      "out_bytes": os.path.getsize(o1) + os.path.getsize(o2), "summary": line})
         print(json.dumps(rows[-1]), file=sys.stderr)
     print(json.dumps({"pairs": args.pairs, "threads": args.threads, "host_cores": os.cpu_count(),
