@@ -1,0 +1,85 @@
+"""Databases that differ from kraken2-build's defaults — read unchanged from their
+three files: other k / l / spaced seeds (window widths the fused kernel does not cover go
+to the warp-per-tile kernels), k == l, minimum_acceptable_hash_value, revcom_version 0,
+another toggle mask, a taxonomy too large for shared memory.  Per-read parity with the oracle."""
+import numpy as np
+import pytest
+
+import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def build(oracle, tmp_path, name, taxonomy=None, genomes=None, **opt_kw):
+    rev = opt_kw.pop("revcom_version", 1)
+    opts = oracle.default_options(**opt_kw)
+    opts.revcom_version = rev
+    genomes = genomes or synth.cfg1_genomes(seed=3, scale=0.004)
+    tax = taxonomy or [oracle.TaxSpec(*t) for t in synth.TAXONOMY_CFG1]
+    db = oracle.OracleDb.build([(t, bytes(g)) for t, g in genomes], tax, opts=opts)
+    d = str(tmp_path / name)
+    db.save(d)
+    db.genomes = genomes
+    return db, d
+
+
+def check(oracle_db, path, fused_expected, paired=True, conf=0.2):
+    from nohuman_b200 import Database, Session
+    seqs = synth.illumina_reads(oracle_db.genomes, 800, 150, seed=8, paired=paired, n_rate=0.1)
+    seqs += synth.ont_reads(oracle_db.genomes, 8, seed=9, n50=1500, max_len=4000)
+    if paired and len(seqs) % 2:
+        seqs.append(seqs[0][:90])
+    bases, offsets = synth.pack(seqs)
+    oracle_db.confidence = conf
+    want = oracle_db.classify_batch(bases, offsets, paired=paired)
+    with Database.open(path, 0) as db, Session(db, confidence=conf, paired=paired) as sess:
+        call, keep, st = sess.classify(bases, offsets)
+        icall, tk, hg = sess.debug_last_batch(len(call))
+        mins, amb, pos_off = sess.debug_minimizers(bases[:int(offsets[40])], offsets[:41])
+    assert bool(st.fused_kernel) == fused_expected
+    np.testing.assert_array_equal(tk, want["total_kmers"])
+    np.testing.assert_array_equal(hg, want["hit_groups"])
+    np.testing.assert_array_equal(icall, want["call"])
+    np.testing.assert_array_equal(call, want["ext"])
+    assert (want["call"] != 0).mean() > 0.3
+    return mins, amb, pos_off, seqs
+
+
+@pytest.mark.parametrize("name,kw,fused", [
+    ("k31_l31", dict(k=31, l=31, spaces=0), False),          # k == l: no window
+    ("k35_l25_s4", dict(k=35, l=25, spaces=4), False),       # window of 11 l-mers
+    ("k25_l21_s3", dict(k=25, l=21, spaces=3), True),        # window of 5 at another k
+    ("no_spaced_seed", dict(spaces=0), True),
+    ("other_toggle", dict(toggle=0x0123456789ABCDEF), True),
+    ("min_hash", dict(min_hash=1 << 62), True),               # a quarter of the minimizers are never looked up
+    ("revcom_v0", dict(revcom_version=0), True),              # pre-2.0.8 reverse complement
+])
+def test_option_variants(oracle, tmp_path, name, kw, fused):
+    db, path = build(oracle, tmp_path, name, **kw)
+    mins, amb, pos_off, seqs = check(db, path, fused)
+    # per-position minimizer stream as well
+    for i in range(40):
+        wm, wa = oracle.scan_positions(db.opts, bytes(seqs[i]))
+        lo, hi = int(pos_off[i]), int(pos_off[i + 1])
+        np.testing.assert_array_equal(amb[lo:hi], wa)
+        np.testing.assert_array_equal(mins[lo:hi][wa == 0], wm[wa == 0])
+
+
+def test_taxonomy_larger_than_shared_memory(oracle, tmp_path):
+    """9000-node taxonomy (value_bits 14): the parent array is read through L2 instead of shared memory"""
+    rng = np.random.default_rng(5)
+    tax = [oracle.TaxSpec(1, 1, "root", "no rank")]
+    ids = [1]
+    for i in range(2, 9001):
+        parent = ids[int(rng.integers(max(0, len(ids) - 40), len(ids)))]  # deep, bushy tree
+        tax.append(oracle.TaxSpec(i, parent, f"n{i}", "no rank"))
+        ids.append(i)
+    leaves = [int(x) for x in rng.choice(np.arange(4000, 9001), size=24, replace=False)]
+    genomes = [(t, synth.random_genome(rng, 6000)) for t in leaves]
+    shared = synth.random_genome(rng, 1500)
+    for _, g in genomes[::2]:
+        g[2000:3500] = shared  # LCA values high up the tree
+    db, path = build(oracle, tmp_path, "bigtax", taxonomy=tax, genomes=genomes)
+    assert db.tax.node_count > 8192 and int(db.cht.value_bits) == 14
+    check(db, path, True, paired=False, conf=0.05)
+    check(db, path, True, paired=True, conf=0.5)
