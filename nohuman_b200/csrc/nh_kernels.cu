@@ -18,6 +18,7 @@
  * src/main.rs:259-265 (--classified-out vs --unclassified-out).
  */
 #include <stdlib.h>
+#include <string.h>
 
 #include "nh_kernels.cuh"
 
@@ -643,18 +644,19 @@ k_score_big(const NhDbParams db, const NhBatchPtrs b, const NhScoreParams sp) {
 
 #define NH_META_DEFERRED 0x80u
 
+#define NH_RING_SLOTS 128u       /* look-ahead ring: two rounds of 32*U lookups */
 #define NH_RING_SKIP 0x80000000u /* below minimum_acceptable_hash_value: no lookup, taxon 0 */
 
 struct __align__(16) FusedWarpSmem {
   /* look-ahead ring: the group's lookups hashed 32 at a time (one per lane) */
-  uint32_t r_unit[64];                   /* aligned group of G sectors holding hash % capacity */
-  uint32_t r_ckey[64];
-  uint32_t r_slot[64];
-  uint32_t r_aux[64];                    /* owner tile | start cell in the group << 5 | NH_RING_SKIP */
-  uint32_t q_unit[32];                   /* continuation queue: next group of sectors to read */
-  uint32_t q_ckey[32];
-  uint32_t q_slot[32];
-  uint32_t q_aux[32];                    /* owner tile | groups visited << 5 */
+  uint32_t r_unit[NH_RING_SLOTS];        /* aligned group of G sectors holding hash % capacity */
+  uint32_t r_ckey[NH_RING_SLOTS];
+  uint32_t r_slot[NH_RING_SLOTS];
+  uint32_t r_aux[NH_RING_SLOTS];         /* owner tile | start cell in the group << 5 | NH_RING_SKIP */
+  uint32_t q_unit[64];                   /* continuation queue: next group of sectors to read */
+  uint32_t q_ckey[64];
+  uint32_t q_slot[64];
+  uint32_t q_aux[64];                    /* owner tile | groups visited << 5 */
   uint32_t prefix[33];                   /* exclusive scan of lookups per tile */
   uint32_t slot[32];                     /* first lookup slot of each tile */
   uint32_t keys[NH_LANE_TAXA * 32];      /* taxon tables, [slot][owner lane] */
@@ -664,8 +666,8 @@ struct __align__(16) FusedWarpSmem {
   uint32_t overflow;                     /* bit per owner lane: table overflowed */
 };
 
-__device__ __forceinline__ uint32_t lane_tab_get(const FusedWarpSmem &sm, uint32_t lane,
-                                                 uint32_t n, uint32_t taxon) {
+template <typename SM>
+__device__ __forceinline__ uint32_t lane_tab_get(const SM &sm, uint32_t lane, uint32_t n, uint32_t taxon) {
   for (uint32_t i = 0; i < n; i++)
     if (sm.keys[i * 32u + lane] == taxon) return sm.cnts[i * 32u + lane];
   return 0;
@@ -674,7 +676,13 @@ __device__ __forceinline__ uint32_t lane_tab_get(const FusedWarpSmem &sm, uint32
 #ifndef NH_FUSED_MIN_BLOCKS
 #define NH_FUSED_MIN_BLOCKS 4
 #endif
-template <int W, int G>
+#ifndef NH_PROBE_DEPTH_DEFAULT
+#define NH_PROBE_DEPTH_DEFAULT 1
+#endif
+#ifndef NH_FUSED_STREAM_DEFAULT
+#define NH_FUSED_STREAM_DEFAULT 0
+#endif
+template <int W, int G, int U>
 __global__ void __launch_bounds__(NH_BLOCK_THREADS, NH_FUSED_MIN_BLOCKS)
 k_scan_probe_score(const NhDbParams db, const NhBatchPtrs b, const NhScoreParams sp) {
   /* G lanes read the G adjacent sectors of one aligned 32*G-byte group with ONE warp
@@ -682,7 +690,9 @@ k_scan_probe_score(const NhDbParams db, const NhBatchPtrs b, const NhScoreParams
    * (profiles/r01_random_access_microbench.txt), so a probe chain that stays inside the
    * group costs nothing extra. */
   static_assert(G == 1 || G == 2 || G == 4, "a group is 32, 64 or 128 bytes");
-  constexpr uint32_t NI = 32u / G;          /* lookups per round */
+  static_assert(U == 1 || U == 2, "sector reads in flight per lane");
+  constexpr uint32_t NI = 32u * U / G;      /* lookups per round */
+  constexpr uint32_t RMASK = NH_RING_SLOTS - 1u;
   constexpr uint32_t GCELLS = 8u * G;       /* cells per group */
   extern __shared__ __align__(16) uint32_t s_dyn[];
   uint32_t *s_parent = s_dyn;
@@ -800,7 +810,9 @@ k_scan_probe_score(const NhDbParams db, const NhBatchPtrs b, const NhScoreParams
           const bool newrun = nonamb && mz != last;
           if (newrun && cnt) {
             out_min[n_runs] = last;
+#ifndef NH_EXP_NO_CNT_STORES
             out_cnt[n_runs] = (uint8_t)cnt;
+#endif
             n_runs++;
           }
           cnt = newrun ? 1u : cnt + (nonamb ? 1u : 0u);
@@ -835,125 +847,155 @@ k_scan_probe_score(const NhDbParams db, const NhBatchPtrs b, const NhScoreParams
     tot_lookups += n_runs;
 
     uint32_t qn = 0, e_next = 0, e_ready = 0;
-    /* hash the next (up to) 32 lookups, one per lane, into the ring */
+    /* hash the next (up to) 32*U lookups, U per lane, into the ring */
     auto prepare = [&]() {
       uint32_t n = total - e_ready;
-      n = n < 32u ? n : 32u;
-      if (lane < n) {
-        const uint32_t e = e_ready + lane;
-        uint32_t o = 0; /* owner tile: largest o with prefix[o] <= e */
+      n = n < 32u * U ? n : 32u * U;
 #pragma unroll
-        for (int step = 16; step >= 1; step >>= 1)
-          if (sm.prefix[o + step] <= e) o += (uint32_t)step;
-        const uint32_t oslot = sm.slot[o] + (e - sm.prefix[o]);
-        const uint64_t h = nh_fmix64(__ldcg(b.lk_min + oslot));
-        uint32_t aux = o | NH_RING_SKIP;
-        if (!(db.min_hash && h < db.min_hash)) {
-          const uint64_t idx = nh_fastmod(h, db.capacity, db.mod_m, db.mod_sh1, db.mod_sh2);
-          sm.r_unit[e & 63u] = (uint32_t)(idx / GCELLS);
-          sm.r_ckey[e & 63u] = (uint32_t)(h >> (32u + db.value_bits));
-          aux = o | ((uint32_t)(idx % GCELLS) << 5);
+      for (int u = 0; u < U; u++) {
+        const uint32_t e = e_ready + (uint32_t)u * 32u + lane;
+        if (e < e_ready + n) {
+          uint32_t o = 0; /* owner tile: largest o with prefix[o] <= e */
+#pragma unroll
+          for (int step = 16; step >= 1; step >>= 1)
+            if (sm.prefix[o + step] <= e) o += (uint32_t)step;
+          const uint32_t oslot = sm.slot[o] + (e - sm.prefix[o]);
+          const uint64_t h = nh_fmix64(__ldcg(b.lk_min + oslot));
+          uint32_t aux = o | NH_RING_SKIP;
+          if (!(db.min_hash && h < db.min_hash)) {
+            const uint64_t idx = nh_fastmod(h, db.capacity, db.mod_m, db.mod_sh1, db.mod_sh2);
+            sm.r_unit[e & RMASK] = (uint32_t)(idx / GCELLS);
+            sm.r_ckey[e & RMASK] = (uint32_t)(h >> (32u + db.value_bits));
+            aux = o | ((uint32_t)(idx % GCELLS) << 5);
+          }
+          sm.r_slot[e & RMASK] = oslot;
+          sm.r_aux[e & RMASK] = aux;
         }
-        sm.r_slot[e & 63u] = oslot;
-        sm.r_aux[e & 63u] = aux;
       }
       e_ready += n;
     };
     prepare();
     __syncwarp();
-    const uint32_t it = lane / G, sub = lane % G;
+    const uint32_t sub = lane % G;
     while (qn != 0u || e_next < total) {
-      bool active = false, skip = false;
-      uint32_t unit = 0, ckey = 0, oslot = 0, aux = 0, start = 0;
-      if (it < qn) {
-        unit = sm.q_unit[it];
-        ckey = sm.q_ckey[it];
-        oslot = sm.q_slot[it];
-        aux = sm.q_aux[it];
-        active = true;
-      } else {
-        const uint32_t e = e_next + (it - qn);
-        if (e < total) {
-          active = true;
-          oslot = sm.r_slot[e & 63u];
-          const uint32_t ra = sm.r_aux[e & 63u];
-          aux = ra & 31u;
-          if (ra & NH_RING_SKIP) {
-            skip = true;
-          } else {
-            unit = sm.r_unit[e & 63u];
-            ckey = sm.r_ckey[e & 63u];
-            start = (ra >> 5) & 31u;
+      /* ---- every lane takes U work items: continuations first, then fresh lookups ---- */
+      bool active[U], skip[U];
+      uint32_t unit[U], ckey[U], oslot[U], aux[U], start[U];
+      uint32_t c[U][8];
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const uint32_t it = (uint32_t)u * (32u / G) + lane / G;
+        active[u] = false;
+        skip[u] = false;
+        unit[u] = ckey[u] = oslot[u] = aux[u] = start[u] = 0;
+        if (it < qn) {
+          unit[u] = sm.q_unit[it];
+          ckey[u] = sm.q_ckey[it];
+          oslot[u] = sm.q_slot[it];
+          aux[u] = sm.q_aux[it];
+          active[u] = true;
+        } else {
+          const uint32_t e = e_next + (it - qn);
+          if (e < total) {
+            active[u] = true;
+            oslot[u] = sm.r_slot[e & RMASK];
+            const uint32_t ra = sm.r_aux[e & RMASK];
+            aux[u] = ra & 31u;
+            if (ra & NH_RING_SKIP) {
+              skip[u] = true;
+            } else {
+              unit[u] = sm.r_unit[e & RMASK];
+              ckey[u] = sm.r_ckey[e & RMASK];
+              start[u] = (ra >> 5) & 31u;
+            }
           }
         }
       }
       e_next += NI - qn;
       if (e_next > total) e_next = total;
-      uint32_t c[8];
-      const bool probing = active && !skip;
-      const uint64_t cell0 = ((uint64_t)unit * G + sub) * 8ULL; /* first cell of this lane's sector */
-      if (probing) ld_sector(db.cells + cell0, c);
-      __syncwarp(); /* queue and ring fully read before they are refilled */
-      if (e_ready < total && e_ready - e_next <= 32u) prepare(); /* its key reads overlap the sector reads */
-      int state = -1;
-      if (probing) {
-        /* cells of this sector the chain may stop at: from `start` on, inside the table */
-        const int lo = (int)start - (int)(sub * 8u);
-        uint32_t range = lo <= 0 ? 0xFFu : (lo >= 8 ? 0u : (0xFFu << lo) & 0xFFu);
-        if (cell0 + 8ULL > db.capacity)
-          range &= cell0 >= db.capacity ? 0u : (1u << (uint32_t)(db.capacity - cell0)) - 1u;
+      /* ---- all sector reads of the round are issued before any is looked at ---- */
 #pragma unroll
-        for (int j = 7; j >= 0; j--) {
-          const uint32_t val = c[j] & db.value_mask;
-          const bool term = (val == 0u) || ((c[j] >> db.value_bits) == ckey);
-          if (term && ((range >> j) & 1u)) state = (int)val;
-        }
-      }
-      /* the first lane of the G that found a terminal cell has the answer */
-      const uint32_t fmask = __ballot_sync(FULL_MASK, state >= 0);
-      const uint32_t gbase = lane & ~(uint32_t)(G - 1);
-      const uint32_t gbits = (fmask >> gbase) & ((1u << G) - 1u);
-      const uint32_t result_any = (uint32_t)__shfl_sync(FULL_MASK, state, gbase + (gbits ? (uint32_t)__ffs(gbits) - 1u : 0u));
-      bool done = skip || gbits != 0u;
-      uint32_t result = gbits ? result_any : 0u;
-      if (active && !done) {
-        const uint32_t visits = (aux >> 5) + 1u;
-        if (visits >= max_visits) {
-          done = true; /* went round a table without an empty cell */
-        } else {
-          aux = (aux & 31u) | (visits << 5);
-          unit = (uint64_t)unit + 1ULL >= n_units ? 0u : unit + 1u;
-        }
-      }
-      const bool leader = active && sub == 0u;
-      const bool cont = leader && !done;
-      const uint32_t cmask = __ballot_sync(FULL_MASK, cont);
-      if (cont) {
-        const uint32_t pos = __popc(cmask & lane_lt);
-        sm.q_unit[pos] = unit;
-        sm.q_ckey[pos] = ckey;
-        sm.q_slot[pos] = oslot;
-        sm.q_aux[pos] = aux;
-      }
-      qn = __popc(cmask);
-      if (leader && done) {
-        const uint32_t mt = sm.meta[aux & 31u];
-        if ((mt & NH_META_DEFERRED) || b.emit_all_taxa) b.lk_taxon[oslot] = result;
-        if (!(mt & NH_META_DEFERRED) && result) {
-          const uint32_t own = mt;
-          const uint32_t n = (uint32_t)__ldcg(b.lk_cnt + oslot);
-          atomicAdd(&sm.groups[own], 1u);
-          int i = 0;
-          for (; i < sp.lane_taxa; i++) {
-            const uint32_t old = atomicCAS(&sm.keys[i * 32 + own], 0u, result);
-            if (old == 0u || old == result) {
-              atomicAdd(&sm.cnts[i * 32 + own], n);
-              break;
-            }
+      for (int u = 0; u < U; u++)
+        if (active[u] && !skip[u]) ld_sector(db.cells + ((uint64_t)unit[u] * G + sub) * 8ULL, c[u]);
+      __syncwarp(); /* queue and ring fully read before they are refilled */
+      if (e_ready < total && e_ready - e_next <= 32u * U) prepare(); /* its key reads overlap the sector reads */
+      uint32_t q_fill = 0;
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const bool probing = active[u] && !skip[u];
+        const uint64_t cell0 = ((uint64_t)unit[u] * G + sub) * 8ULL; /* first cell of this lane's sector */
+        int state = -1;
+        if (probing) {
+          /* cells of this sector the chain may stop at: from `start` on, inside the table */
+          const int lo = (int)start[u] - (int)(sub * 8u);
+          uint32_t range = lo <= 0 ? 0xFFu : (lo >= 8 ? 0u : (0xFFu << lo) & 0xFFu);
+          if (cell0 + 8ULL > db.capacity)
+            range &= cell0 >= db.capacity ? 0u : (1u << (uint32_t)(db.capacity - cell0)) - 1u;
+#pragma unroll
+          for (int j = 7; j >= 0; j--) {
+            const uint32_t val = c[u][j] & db.value_mask;
+            const bool term = (val == 0u) || ((c[u][j] >> db.value_bits) == ckey[u]);
+            if (term && ((range >> j) & 1u)) state = (int)val;
           }
-          if (i == sp.lane_taxa) atomicOr(&sm.overflow, 1u << own);
+        }
+        bool done = skip[u];
+        uint32_t result = 0;
+        if (G == 1) {
+          if (state >= 0) {
+            done = true;
+            result = (uint32_t)state;
+          }
+        } else {
+          /* the first lane of the G that found a terminal cell has the answer */
+          const uint32_t fmask = __ballot_sync(FULL_MASK, state >= 0);
+          const uint32_t gbase = lane & ~(uint32_t)(G - 1);
+          const uint32_t gbits = (fmask >> gbase) & ((1u << G) - 1u);
+          const uint32_t any = (uint32_t)__shfl_sync(FULL_MASK, state, gbase + (gbits ? (uint32_t)__ffs(gbits) - 1u : 0u));
+          if (gbits) {
+            done = true;
+            result = any;
+          }
+        }
+        if (active[u] && !done) {
+          const uint32_t visits = (aux[u] >> 5) + 1u;
+          if (visits >= max_visits) {
+            done = true; /* went round a table without an empty cell */
+          } else {
+            aux[u] = (aux[u] & 31u) | (visits << 5);
+            unit[u] = (uint64_t)unit[u] + 1ULL >= n_units ? 0u : unit[u] + 1u;
+          }
+        }
+        const bool leader = active[u] && sub == 0u;
+        const bool cont = leader && !done;
+        const uint32_t cmask = __ballot_sync(FULL_MASK, cont);
+        if (cont) {
+          const uint32_t pos = q_fill + __popc(cmask & lane_lt);
+          sm.q_unit[pos] = unit[u];
+          sm.q_ckey[pos] = ckey[u];
+          sm.q_slot[pos] = oslot[u];
+          sm.q_aux[pos] = aux[u];
+        }
+        q_fill += __popc(cmask);
+        if (leader && done) {
+          const uint32_t mt = sm.meta[aux[u] & 31u];
+          if ((mt & NH_META_DEFERRED) || b.emit_all_taxa) b.lk_taxon[oslot[u]] = result;
+          if (!(mt & NH_META_DEFERRED) && result) {
+            const uint32_t own = mt;
+            const uint32_t n = (uint32_t)__ldcg(b.lk_cnt + oslot[u]);
+            atomicAdd(&sm.groups[own], 1u);
+            int i = 0;
+            for (; i < sp.lane_taxa; i++) {
+              const uint32_t old = atomicCAS(&sm.keys[i * 32 + own], 0u, result);
+              if (old == 0u || old == result) {
+                atomicAdd(&sm.cnts[i * 32 + own], n);
+                break;
+              }
+            }
+            if (i == sp.lane_taxa) atomicOr(&sm.overflow, 1u << own);
+          }
         }
       }
+      qn = q_fill;
       __syncwarp();
     }
 
@@ -975,6 +1017,381 @@ k_scan_probe_score(const NhDbParams db, const NhBatchPtrs b, const NhScoreParams
           if (len >= (uint64_t)k) total_kmers += (uint32_t)(len - (uint64_t)k + 1);
         }
         /* ResolveTree */
+        uint32_t best_s = 0, best_t = 0;
+        for (uint32_t i = 0; i < ntab; i++) {
+          const uint32_t tx = sm.keys[i * 32u + lane];
+          uint32_t score = 0;
+          for (uint32_t a = tx; a; a = parent[a]) score += lane_tab_get(sm, lane, ntab, a);
+          if (score > best_s) {
+            best_s = score;
+            best_t = tx;
+          } else if (score == best_s) {
+            best_t = lca(parent, best_t, tx);
+          }
+        }
+        uint32_t max_taxon = best_t;
+        uint32_t max_score = max_taxon ? lane_tab_get(sm, lane, ntab, max_taxon) : 0u;
+        const uint32_t required = (uint32_t)ceil(__dmul_rn(sp.confidence, (double)total_kmers));
+        while (max_taxon && max_score < required) {
+          uint32_t sum = 0;
+          for (uint32_t i = 0; i < ntab; i++)
+            if (is_a_ancestor_of_b(parent, max_taxon, sm.keys[i * 32u + lane]))
+              sum += sm.cnts[i * 32u + lane];
+          max_score = sum;
+          if (max_score >= required) break;
+          max_taxon = parent[max_taxon];
+        }
+        uint32_t call = max_taxon;
+        if (call && groups < sp.min_hit_groups) call = 0;
+        const uint32_t is_cls = call != 0u;
+        const uint32_t keep = sp.keep_human ? is_cls : !is_cls;
+        if (b.out_call) b.out_call[u] = call ? db.ext_id[call] : 0u;
+        if (b.out_keep) b.out_keep[u] = (uint8_t)keep;
+        if (b.dbg_call) b.dbg_call[u] = call;
+        if (b.dbg_total_kmers) b.dbg_total_kmers[u] = total_kmers;
+        if (b.dbg_hit_groups) b.dbg_hit_groups[u] = (uint32_t)groups;
+        tot_classified += is_cls;
+        tot_kept += keep;
+      }
+    }
+    __syncwarp();
+  }
+  tot_lookups = warp_sum_u32(tot_lookups);
+  tot_classified = warp_sum_u32(tot_classified);
+  tot_kept = warp_sum_u32(tot_kept);
+  if (lane == 0) {
+    if (tot_lookups) atomicAdd(&b.counters->n_lookups, tot_lookups);
+    if (tot_classified) atomicAdd(&b.counters->n_classified, tot_classified);
+    if (tot_kept) atomicAdd(&b.counters->n_kept, tot_kept);
+  }
+}
+
+/* ------------------------------------------------------------------ */
+/* fused path, streaming form: the scan feeds the probe through shared memory */
+/*
+ * Same work as k_scan_probe_score, different schedule.  There the 32 lanes
+ * scan their whole tiles first and park every lookup in global memory; each
+ * of those scattered 8-byte and 1-byte stores is its own memory request, and
+ * requests are what this path is short of.  Here a closed run
+ * goes straight into a small queue in shared memory; whenever 32 lookups are
+ * waiting the warp hashes them and issues their sector reads, then goes back
+ * to scanning.  The sectors are looked at one probe round later, i.e. after
+ * the warp has scanned further, so the scan's integer work hides the
+ * table's latency inside one warp instead of relying on other warps.
+ * Tiles of deferred units (long reads) and sessions with emit_runs still get
+ * their lookups written to global memory for k_score / k_gather_runs.
+ */
+
+struct __align__(16) StreamWarpSmem {
+  uint64_t pq_key[128];                  /* closed runs waiting to be probed (ring) */
+  uint32_t pq_slot[128];
+  uint16_t pq_meta[128];                 /* owner lane | k-mer count << 5 */
+  uint32_t q_unit[64];                   /* probe chains that continue into the next sector */
+  uint32_t q_ckey[64];
+  uint32_t q_slot[64];
+  uint32_t q_aux[64];                    /* owner lane | k-mer count << 5 | sectors visited << 13 */
+  uint32_t keys[NH_LANE_TAXA * 32];      /* taxon tables, [slot][owner lane] */
+  uint32_t cnts[NH_LANE_TAXA * 32];
+  uint32_t groups[32];                   /* minimizer_hit_groups per owner lane */
+  uint8_t meta[32];                      /* per tile: owner lane | NH_META_DEFERRED */
+  uint32_t overflow;                     /* bit per owner lane: table overflowed */
+};
+
+#define NH_AUX_NONE 0xFFFFFFFFu
+
+template <int W>
+__global__ void __launch_bounds__(NH_BLOCK_THREADS, NH_FUSED_MIN_BLOCKS)
+k_stream_classify(const NhDbParams db, const NhBatchPtrs b, const NhScoreParams sp) {
+  static_assert(W == 5, "the scan consumes one 4-byte word per ring rotation");
+  extern __shared__ __align__(16) uint32_t s_dyn[];
+  uint32_t *s_parent = s_dyn;
+  const bool smem_parent = db.node_count <= NH_SMEM_PARENT_MAX;
+  const uint32_t parent_words = smem_parent ? db.node_count : 0u;
+  StreamWarpSmem *s_warps = reinterpret_cast<StreamWarpSmem *>(s_dyn + ((parent_words + 3u) & ~3u));
+  if (smem_parent) {
+    for (uint32_t i = threadIdx.x; i < db.node_count; i += blockDim.x) s_parent[i] = db.parent[i];
+    __syncthreads();
+  }
+  const uint32_t *parent = smem_parent ? s_parent : db.parent;
+  const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+  const uint32_t lane_lt = (1u << lane) - 1u;
+  StreamWarpSmem &sm = s_warps[warp];
+  const uint32_t n_tiles = b.counters->n_tiles;
+  const int k = db.k, l = db.l;
+  const uint64_t lmask = (1ULL << (2 * l)) - 1ULL;
+  const uint32_t rc_shift = 2u * (uint32_t)(l - 1);
+  const uint64_t n_sectors = (db.capacity + 7ULL) >> 3;
+  /* probe-chain guard for a table without any empty cell (never a real database) */
+  const uint32_t max_visits = n_sectors + 1ULL < 0x7FFFFULL ? (uint32_t)(n_sectors + 1ULL) : 0x7FFFFu;
+  uint32_t tot_lookups = 0, tot_classified = 0, tot_kept = 0;
+
+  for (uint32_t group = blockIdx.x * NH_WARPS_PER_BLOCK + warp; group * 32u < n_tiles;
+       group += gridDim.x * NH_WARPS_PER_BLOCK) {
+    const uint32_t tile = group * 32u + lane;
+    const bool have = tile < n_tiles;
+    NhTile t;
+    t.seq = 0; t.pos_begin = 0; t.slot = 0; t.role = NH_ROLE_DEFERRED;
+    if (have) t = b.tiles[tile];
+#pragma unroll
+    for (int i = 0; i < NH_LANE_TAXA; i++) {
+      sm.keys[i * 32 + lane] = 0;
+      sm.cnts[i * 32 + lane] = 0;
+    }
+    sm.groups[lane] = 0;
+    if (lane == 0) sm.overflow = 0;
+    sm.meta[lane] = (uint8_t)(t.role == NH_ROLE_DEFERRED ? NH_META_DEFERRED
+                              : (t.role == NH_ROLE_PARTNER ? lane - 1u : lane));
+    /* lookups of this tile that other kernels read later go to global memory as well */
+    const bool spill_runs = t.role == NH_ROLE_DEFERRED || b.emit_all_taxa;
+    __syncwarp();
+
+    /* warp-uniform queue state */
+    uint32_t pq_head = 0, pq_n = 0, cq_n = 0;
+    /* the lookup this lane has in flight: its sector is in c[], looked at in the next round */
+    uint32_t c[8];
+    uint32_t f_unit = 0, f_ckey = 0, f_slot = 0, f_aux = NH_AUX_NONE, f_start = 0;
+    bool any_inflight = false; /* warp-uniform */
+
+    /* one probe round: finish the lookups in flight, then put up to 32 waiting ones in flight */
+    auto probe_round = [&]() {
+      /* ---- 1. look at the sectors issued last round ---- */
+      if (any_inflight) {
+        const bool active = f_aux != NH_AUX_NONE;
+        bool done = false;
+        uint32_t result = 0;
+        if (active) {
+          const uint64_t cell0 = (uint64_t)f_unit * 8ULL;
+          uint32_t range = 0xFFu << f_start;
+          if (cell0 + 8ULL > db.capacity) range &= (1u << (uint32_t)(db.capacity - cell0)) - 1u;
+          int state = -1;
+#pragma unroll
+          for (int j = 7; j >= 0; j--) {
+            const uint32_t val = c[j] & db.value_mask;
+            const bool term = (val == 0u) || ((c[j] >> db.value_bits) == f_ckey);
+            if (term && ((range >> j) & 1u)) state = (int)val;
+          }
+          if (state >= 0) {
+            done = true;
+            result = (uint32_t)state;
+          } else {
+            const uint32_t visits = (f_aux >> 13) + 1u;
+            if (visits >= max_visits) {
+              done = true; /* went round a table without an empty cell */
+            } else {
+              f_aux = (f_aux & 0x1FFFu) | (visits << 13);
+              f_unit = (uint64_t)f_unit + 1ULL >= n_sectors ? 0u : f_unit + 1u;
+            }
+          }
+        }
+        const bool cont = active && !done;
+        const uint32_t cmask = __ballot_sync(FULL_MASK, cont);
+        if (cont) {
+          const uint32_t pos = cq_n + __popc(cmask & lane_lt);
+          sm.q_unit[pos] = f_unit;
+          sm.q_ckey[pos] = f_ckey;
+          sm.q_slot[pos] = f_slot;
+          sm.q_aux[pos] = f_aux;
+        }
+        cq_n += __popc(cmask);
+        if (active && done) {
+          const uint32_t own_lane = f_aux & 31u;
+          const uint32_t mt = sm.meta[own_lane];
+          if ((mt & NH_META_DEFERRED) || b.emit_all_taxa) b.lk_taxon[f_slot] = result;
+          if (!(mt & NH_META_DEFERRED) && result) {
+            const uint32_t own = mt;
+            const uint32_t n = (f_aux >> 5) & 0xFFu;
+            atomicAdd(&sm.groups[own], 1u);
+            int i = 0;
+            for (; i < sp.lane_taxa; i++) {
+              const uint32_t old = atomicCAS(&sm.keys[i * 32 + own], 0u, result);
+              if (old == 0u || old == result) {
+                atomicAdd(&sm.cnts[i * 32 + own], n);
+                break;
+              }
+            }
+            if (i == sp.lane_taxa) atomicOr(&sm.overflow, 1u << own);
+          }
+        }
+        __syncwarp(); /* continuation queue written before it is read below */
+      }
+      /* ---- 2. next 32 lookups: continuations first, then fresh runs ---- */
+      const uint32_t n_cq = cq_n < 32u ? cq_n : 32u;
+      const uint32_t room = 32u - n_cq;
+      const uint32_t n_pq = pq_n < room ? pq_n : room;
+      f_aux = NH_AUX_NONE;
+      f_start = 0;
+      if (lane < n_cq) {
+        const uint32_t i = cq_n - 1u - lane; /* newest first: the queue stays a stack, no holes */
+        f_unit = sm.q_unit[i];
+        f_ckey = sm.q_ckey[i];
+        f_slot = sm.q_slot[i];
+        f_aux = sm.q_aux[i];
+      } else if (lane - n_cq < n_pq) {
+        const uint32_t i = (pq_head + (lane - n_cq)) & 127u;
+        const uint64_t h = nh_fmix64(sm.pq_key[i]);
+        f_slot = sm.pq_slot[i];
+        const uint32_t meta = sm.pq_meta[i];
+        if (db.min_hash && h < db.min_hash) {
+          /* below minimum_acceptable_hash_value: kraken2 skips the lookup, taxon 0 */
+          if ((sm.meta[meta & 31u] & NH_META_DEFERRED) || b.emit_all_taxa) b.lk_taxon[f_slot] = 0u;
+        } else {
+          const uint64_t idx = nh_fastmod(h, db.capacity, db.mod_m, db.mod_sh1, db.mod_sh2);
+          f_unit = (uint32_t)(idx >> 3);
+          f_start = (uint32_t)idx & 7u;
+          f_ckey = (uint32_t)(h >> (32u + db.value_bits));
+          f_aux = meta; /* owner | count << 5, zero sectors visited */
+        }
+      }
+      cq_n -= n_cq;
+      pq_head = (pq_head + n_pq) & 127u;
+      pq_n -= n_pq;
+      if (f_aux != NH_AUX_NONE) ld_sector(db.cells + (uint64_t)f_unit * 8ULL, c);
+      any_inflight = (n_cq + n_pq) != 0u;
+      __syncwarp(); /* queue slots just read may be overwritten by the next pushes */
+    };
+
+    /* ---------------- scan, feeding the probe ---------------- */
+    /* Pass 0 is the real one.  Pass 1 runs only if a unit hit more distinct taxa than its
+     * in-warp table holds (warp-uniform, rare): the lanes of such units scan again and write
+     * their lookups to global memory, where k_score_big finds them. */
+    uint32_t n_runs = 0;
+    bool redo_lane = false;
+    for (int pass = 0; pass < 2; pass++) {
+      const bool rescan = pass == 1;
+      const bool scanning = rescan ? redo_lane : have;
+      const bool spill = rescan ? true : spill_runs;
+      n_runs = 0;
+      uint64_t so = 0;
+      uint32_t nb = 0; /* bases of this lane's tile */
+      if (scanning) {
+        so = b.offsets[t.seq];
+        const uint32_t len = (uint32_t)(b.offsets[t.seq + 1] - so);
+        uint32_t npos = len - (uint32_t)k + 1u - t.pos_begin;
+        if (npos > (uint32_t)db.tile_pos) npos = (uint32_t)db.tile_pos;
+        nb = npos + (uint32_t)k - 1u;
+      }
+      const uint8_t *g = b.bases + so + t.pos_begin;
+      const uint32_t mis = (uint32_t)((uintptr_t)g & 3u);
+      const uint32_t *q = reinterpret_cast<const uint32_t *>(g - mis);
+      const uint32_t my_words = scanning ? (mis + nb + 3u) >> 2 : 0u;
+      const uint32_t max_words = __reduce_max_sync(FULL_MASK, my_words);
+
+      uint64_t fwd = 0, rc = 0;
+      uint64_t ring[4];
+#pragma unroll
+      for (int i = 0; i < 4; i++) ring[i] = NH_NONE64;
+      uint32_t c_run = 0;           /* consecutive unambiguous bases ending here */
+      uint64_t last = NH_NONE64;    /* minimizer of the open run */
+      uint32_t cnt = 0;             /* k-mer positions in the open run */
+      const bool dbg = b.dbg_pos_min != nullptr && !rescan;
+      const uint64_t dbg_base = dbg && scanning ? b.dbg_pos_offsets[t.seq] + t.pos_begin : 0;
+      const uint32_t first_pos = mis + (uint32_t)(k - 1);
+      const uint32_t end_idx = mis + nb;
+
+      /* a closed run: to the shared queue (and to global memory when another kernel needs it) */
+      auto emit = [&](bool pred, uint64_t key, uint32_t count) {
+        const uint32_t slot = t.slot + n_runs;
+        if (!rescan) {
+          const uint32_t emask = __ballot_sync(FULL_MASK, pred);
+          if (pred) {
+            const uint32_t i = (pq_head + pq_n + __popc(emask & lane_lt)) & 127u;
+            sm.pq_key[i] = key;
+            sm.pq_slot[i] = slot;
+            sm.pq_meta[i] = (uint16_t)(lane | (count << 5));
+          }
+          pq_n += __popc(emask);
+        }
+        if (pred) {
+          if (spill) {
+            b.lk_min[slot] = key;
+            b.lk_cnt[slot] = (uint8_t)count;
+          }
+          n_runs++;
+        }
+      };
+
+      uint32_t codes = 0, ambs = 0;
+      uint32_t w_next = my_words ? __ldg(q) : 0u; /* loaded one word ahead of its use */
+      for (uint32_t base_i = 0; base_i < max_words * 4u; base_i += 4u) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const uint32_t i = base_i + (uint32_t)j; /* index in the word-aligned stream */
+          if (j == 0) {
+            codes = nh_pack4(w_next, &ambs); /* first base in bits 7..6 */
+            const uint32_t wi = (base_i >> 2) + 1u;
+            w_next = wi < my_words ? __ldg(q + wi) : 0u;
+          }
+          const uint32_t cc = (codes >> (6u - 2u * (uint32_t)j)) & 3u;
+          const bool inside = i >= mis && i < end_idx;
+          /* bytes outside the tile count as ambiguous: they reset the l-mer and never reach a position */
+          const bool amb = ((ambs >> j) & 1u) || !inside;
+          fwd = ((fwd << 2) | cc) & lmask;
+          rc = (rc >> 2) | ((uint64_t)(3u - cc) << rc_shift);
+          c_run = amb ? 0u : c_run + 1u;
+          uint64_t cand = NH_NONE64;
+          if (c_run >= (uint32_t)l) {
+            const uint64_t rcv = db.revcom_version == 0
+                                     ? (((rc << (64 - 2 * l)) | ((1ULL << (64 - 2 * l)) - 1ULL)) & lmask)
+                                     : rc;
+            cand = ((fwd < rcv ? fwd : rcv) & db.seed_mask) ^ db.toggle;
+          }
+          uint64_t m = cand;
+#pragma unroll
+          for (int r = 0; r < 4; r++) m = min_u64(m, ring[r]);
+#pragma unroll
+          for (int r = 3; r > 0; r--) ring[r] = ring[r - 1];
+          ring[0] = cand;
+          const bool at_pos = inside && i >= first_pos;
+          const bool nonamb = at_pos && c_run >= (uint32_t)db.amb_span;
+          const uint64_t mz = m ^ db.toggle;
+          if (dbg && at_pos) {
+            const uint64_t o = dbg_base + (i - first_pos);
+            b.dbg_pos_min[o] = mz;
+            b.dbg_pos_ambig[o] = nonamb ? 0 : 1;
+          }
+          const bool newrun = nonamb && mz != last;
+          emit(newrun && cnt != 0u, last, cnt);
+          cnt = newrun ? 1u : cnt + (nonamb ? 1u : 0u);
+          last = newrun ? mz : last;
+          if (j & 1) {
+            while (pq_n + cq_n >= 32u) probe_round();
+          }
+        }
+      }
+      emit(cnt != 0u, last, cnt);
+      if (scanning) {
+        NhTileOut o;
+        o.lk_off = t.slot;
+        o.lk_cnt = n_runs;
+        b.tile_out[tile] = o;
+      }
+      if (rescan) break;
+      tot_lookups += n_runs;
+      /* drain: whatever is waiting or in flight */
+      while (pq_n + cq_n != 0u || any_inflight) probe_round();
+      const uint32_t ov = sm.overflow; /* final: every fold happened before the last __syncwarp */
+      if (ov == 0u) break;
+      redo_lane = have && ((t.role == NH_ROLE_PARTNER ? (ov >> (lane - 1u)) : (ov >> lane)) & 1u) &&
+                  t.role != NH_ROLE_DEFERRED && !spill_runs;
+    }
+
+    /* ---------------- score short units in the warp ---------------- */
+    if (have && (t.role == NH_ROLE_LEADER || t.role == NH_ROLE_LEADER2)) {
+      const uint32_t u = b.paired ? (t.seq >> 1) : t.seq;
+      if ((sm.overflow >> lane) & 1u) {
+        /* more distinct taxa than a lane table holds: k_score_big probes the unit again;
+         * it needs the lookups in global memory, which only spilled tiles have */
+        b.overflow_units[atomicAdd(&b.counters->n_overflow, 1u)] = u | NH_OVERFLOW_REPROBE;
+      } else {
+        uint32_t ntab = 0;
+        while (ntab < (uint32_t)sp.lane_taxa && sm.keys[ntab * 32u + lane] != 0u) ntab++;
+        const int groups = (int)sm.groups[lane];
+        const uint32_t s0 = b.paired ? (t.seq & ~1u) : t.seq;
+        uint32_t total_kmers = 0;
+        for (uint32_t mm = 0; mm < (b.paired ? 2u : 1u); mm++) {
+          const uint64_t len = b.offsets[s0 + mm + 1] - b.offsets[s0 + mm];
+          if (len >= (uint64_t)k) total_kmers += (uint32_t)(len - (uint64_t)k + 1);
+        }
         uint32_t best_s = 0, best_t = 0;
         for (uint32_t i = 0; i < ntab; i++) {
           const uint32_t tx = sm.keys[i * 32u + lane];
@@ -1078,11 +1495,16 @@ cudaError_t nh_kernels_init(void) {
                            NH_SMEM_PARENT_MAX * 4 + NH_WARPS_PER_BLOCK * NH_WARP_HASH_SLOTS * 8);
   if (e != cudaSuccess) return e;
   const int fused_max = NH_SMEM_PARENT_MAX * 4 + NH_WARPS_PER_BLOCK * (int)sizeof(FusedWarpSmem);
-  e = cudaFuncSetAttribute(k_scan_probe_score<5, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused_max);
+  e = cudaFuncSetAttribute(k_stream_classify<5>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           NH_SMEM_PARENT_MAX * 4 + NH_WARPS_PER_BLOCK * (int)sizeof(StreamWarpSmem));
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(k_scan_probe_score<5, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused_max);
+  e = cudaFuncSetAttribute(k_scan_probe_score<5, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused_max);
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(k_scan_probe_score<5, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused_max);
+  e = cudaFuncSetAttribute(k_scan_probe_score<5, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused_max);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(k_scan_probe_score<5, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused_max);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(k_scan_probe_score<5, 4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused_max);
   if (e != cudaSuccess) return e;
   g_big_smem_ok = 1;
   return cudaSuccess;
@@ -1117,19 +1539,37 @@ int nh_launch_fused(const NhDbParams &db, const NhBatchPtrs &b, const NhScorePar
   if (grid == 0) grid = 1;
   /* NH_PROBE_LANES=1|2|4: lanes (adjacent sectors) per lookup.  2 and 4 cut the requests per
    * lookup from 1.41 to 1.24 / 1.12 but cost more issue slots than they save (measured:
-   * 3.67 / 3.81 / 5.27 ms per 1 M pairs), so the default is 1. */
-  static int lanes = 0;
+   * 3.67 / 3.81 / 5.27 ms per 1 M pairs), so the default is 1.
+   * NH_PROBE_DEPTH=1|2: sector reads in flight per lane and round. */
+  static int lanes = 0, depth = 0;
   if (!lanes) {
     const char *e = getenv("NH_PROBE_LANES");
     lanes = e ? atoi(e) : 1;
     if (lanes != 1 && lanes != 2 && lanes != 4) lanes = 1;
+    const char *d = getenv("NH_PROBE_DEPTH");
+    depth = d ? atoi(d) : NH_PROBE_DEPTH_DEFAULT;
+    if (depth != 1 && depth != 2) depth = NH_PROBE_DEPTH_DEFAULT;
   }
-  if (lanes == 1)
-    k_scan_probe_score<5, 1><<<grid, NH_BLOCK_THREADS, fused_smem_bytes(db), st>>>(db, b, sp);
+  static int stream = -1; /* NH_FUSED_KERNEL=stream|phased */
+  if (stream < 0) {
+    const char *e = getenv("NH_FUSED_KERNEL");
+    stream = e ? (strcmp(e, "stream") == 0) : NH_FUSED_STREAM_DEFAULT;
+  }
+  if (stream) {
+    const uint32_t parent_words = db.node_count <= NH_SMEM_PARENT_MAX ? db.node_count : 0u;
+    const size_t ssmem = (size_t)((parent_words + 3u) & ~3u) * 4 + NH_WARPS_PER_BLOCK * sizeof(StreamWarpSmem);
+    k_stream_classify<5><<<grid, NH_BLOCK_THREADS, ssmem, st>>>(db, b, sp);
+    return 1;
+  }
+  const size_t smem = fused_smem_bytes(db);
+  if (lanes == 1 && depth == 2)
+    k_scan_probe_score<5, 1, 2><<<grid, NH_BLOCK_THREADS, smem, st>>>(db, b, sp);
+  else if (lanes == 1)
+    k_scan_probe_score<5, 1, 1><<<grid, NH_BLOCK_THREADS, smem, st>>>(db, b, sp);
   else if (lanes == 2)
-    k_scan_probe_score<5, 2><<<grid, NH_BLOCK_THREADS, fused_smem_bytes(db), st>>>(db, b, sp);
+    k_scan_probe_score<5, 2, 1><<<grid, NH_BLOCK_THREADS, smem, st>>>(db, b, sp);
   else
-    k_scan_probe_score<5, 4><<<grid, NH_BLOCK_THREADS, fused_smem_bytes(db), st>>>(db, b, sp);
+    k_scan_probe_score<5, 4, 1><<<grid, NH_BLOCK_THREADS, smem, st>>>(db, b, sp);
   return 1;
 }
 
