@@ -680,7 +680,7 @@ __device__ __forceinline__ uint32_t lane_tab_get(const SM &sm, uint32_t lane, ui
 #define NH_PROBE_DEPTH_DEFAULT 1
 #endif
 #ifndef NH_FUSED_STREAM_DEFAULT
-#define NH_FUSED_STREAM_DEFAULT 0
+#define NH_FUSED_STREAM_DEFAULT 1
 #endif
 template <int W, int G, int U>
 __global__ void __launch_bounds__(NH_BLOCK_THREADS, NH_FUSED_MIN_BLOCKS)
@@ -1099,8 +1099,14 @@ struct __align__(16) StreamWarpSmem {
 
 #define NH_AUX_NONE 0xFFFFFFFFu
 
+/* 3 blocks of 8 warps per SM (up to 85 registers): with the overlap happening inside the warp,
+ * registers are worth more than resident warps (measured 3.14 ms at 80 registers / 24 warps
+ * against 3.35 ms at 64 / 32 and 3.38 ms at 103 / 16) */
+#ifndef NH_STREAM_MIN_BLOCKS
+#define NH_STREAM_MIN_BLOCKS 3
+#endif
 template <int W>
-__global__ void __launch_bounds__(NH_BLOCK_THREADS, NH_FUSED_MIN_BLOCKS)
+__global__ void __launch_bounds__(NH_BLOCK_THREADS, NH_STREAM_MIN_BLOCKS)
 k_stream_classify(const NhDbParams db, const NhBatchPtrs b, const NhScoreParams sp) {
   static_assert(W == 5, "the scan consumes one 4-byte word per ring rotation");
   extern __shared__ __align__(16) uint32_t s_dyn[];
@@ -1353,8 +1359,16 @@ k_stream_classify(const NhDbParams db, const NhBatchPtrs b, const NhScoreParams 
           emit(newrun && cnt != 0u, last, cnt);
           cnt = newrun ? 1u : cnt + (nonamb ? 1u : 0u);
           last = newrun ? mz : last;
-          if (j & 1) {
+#ifndef NH_STREAM_CHECK_MASK
+#define NH_STREAM_CHECK_MASK 1 /* probe check after bases with (j & mask) == mask: 1 -> every 2nd base */
+#endif
+          if ((j & NH_STREAM_CHECK_MASK) == NH_STREAM_CHECK_MASK) {
+#ifdef NH_STREAM_SINGLE_ROUND
+            if (pq_n + cq_n >= 32u) probe_round();
+            while (pq_n > 64u) probe_round();
+#else
             while (pq_n + cq_n >= 32u) probe_round();
+#endif
           }
         }
       }
@@ -1556,6 +1570,9 @@ int nh_launch_fused(const NhDbParams &db, const NhBatchPtrs &b, const NhScorePar
     stream = e ? (strcmp(e, "stream") == 0) : NH_FUSED_STREAM_DEFAULT;
   }
   if (stream) {
+    const uint32_t smax = (uint32_t)sm_count * NH_STREAM_MIN_BLOCKS;
+    grid = blocks < smax ? blocks : smax;
+    if (grid == 0) grid = 1;
     const uint32_t parent_words = db.node_count <= NH_SMEM_PARENT_MAX ? db.node_count : 0u;
     const size_t ssmem = (size_t)((parent_words + 3u) & ~3u) * 4 + NH_WARPS_PER_BLOCK * sizeof(StreamWarpSmem);
     k_stream_classify<5><<<grid, NH_BLOCK_THREADS, ssmem, st>>>(db, b, sp);
