@@ -294,6 +294,7 @@ def main():
     stage = {"plan": 0.0, "minimizer": 0.0, "probe": 0.0, "score": 0.0}
     lookups = tiles = launches = classified = 0
     fused = False
+    fused_form = 0
     barrier()
     tok = sampler.mark()
     torch.cuda.cudart().cudaProfilerStart()  # `ncu --profile-from-start off` sees the timed steps only
@@ -309,6 +310,7 @@ def main():
         launches += st.gpu_launches
         classified += st.n_classified
         fused = bool(st.fused_kernel)
+        fused_form = int(st.fused_kernel)
     ev1.record(ext)
     barrier()
     torch.cuda.cudart().cudaProfilerStop()
@@ -342,9 +344,9 @@ def main():
     staging = lk_per_step * 13.0  # 8 B key + 1 B run length + 4 B taxon per lookup (L2-resident scratch)
     if fused:
         # one kernel: 1 B/base read + one 32 B sector per lookup + 5 B/unit of results
-        stage = {"plan": stage["plan"], "scan_probe_score": stage["minimizer"], "score_deferred": stage["score"]}
-        alg = {"scan_probe_score": total * 1.0 + lk_per_step * 32.0 + n_pairs * 5.0,
-               "score_deferred": 0.0, "plan": n_seqs * 8.0}
+        fname = "stream_classify" if fused_form == 2 else "scan_probe_score"
+        stage = {"plan": stage["plan"], fname: stage["minimizer"], "score_deferred": stage["score"]}
+        alg = {fname: total * 1.0 + lk_per_step * 32.0 + n_pairs * 5.0, "score_deferred": 0.0, "plan": n_seqs * 8.0}
     else:
         alg = {
             # minimizer: 1 B/base read + 9 B per lookup written (8 B key + 1 B k-mer count) + 8 B/tile
@@ -355,7 +357,7 @@ def main():
             "plan": n_seqs * 8.0,
         }
     dom = max(stage, key=lambda k_: stage[k_])
-    probe_name = "scan_probe_score" if fused else "probe"
+    probe_name = ("stream_classify" if fused_form == 2 else "scan_probe_score") if fused else "probe"
 
     traffic_tab = {}
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
@@ -403,7 +405,7 @@ def main():
         },
         "reads_per_s": round(reads_s, 1),
         "stage_ms": {k_: round(v, 4) for k_, v in stage.items()},
-        "lookups_per_step": int(lk_per_step), "kernel_path": "fused" if fused else "warp-per-tile",
+        "lookups_per_step": int(lk_per_step), "kernel_path": {0: "warp-per-tile", 1: "fused (phased)", 2: "fused (streaming)"}[fused_form],
         "classified_frac": round(classified / (args.steps * n_pairs), 4),
         "gpu_launches": int(launches),
         "clocks": clocks,

@@ -93,7 +93,7 @@ typedef struct {
   float ms_plan, ms_minimizer, ms_probe, ms_score;
   float ms_h2d, ms_d2h;
   uint32_t gpu_launches;   /* kernels launched for this batch */
-  uint32_t fused_kernel;   /* 1: k_scan_probe_score path, 0: warp-per-tile kernels */
+  uint32_t fused_kernel;   /* 0: warp-per-tile kernels, 1: k_scan_probe_score, 2: k_stream_classify */
 } nh_batch_stats_t;
 
 typedef struct {

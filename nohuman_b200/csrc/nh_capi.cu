@@ -646,7 +646,9 @@ static int enqueue_batch(nh_session *s, const uint8_t *d_bases, const uint64_t *
   cudaEventRecord(s->ev[EV_MIN0], st);
   if (fused) {
     /* scan + probe + in-warp scoring of short units in one kernel; ms_probe reads 0 */
-    launches += nh_launch_fused(P, B, SP, (uint32_t)tiles_upper, sm, st);
+    /* mean sequence length decides the form of the fused kernel: single-tile reads stream */
+    const bool short_reads = total_bases <= n_seqs * (uint64_t)(P.tile_pos + P.k - 1);
+    launches += nh_launch_fused(P, B, SP, (uint32_t)tiles_upper, sm, short_reads, st, &s->last_form);
     cudaEventRecord(s->ev[EV_PROBE0], st);
   } else {
     launches += nh_launch_minimizers(P, B, (uint32_t)tiles_upper, sm, st);
@@ -710,7 +712,7 @@ extern "C" int nh_session_sync(nh_session *s, nh_batch_stats_t *stats) {
         cudaEventElapsedTime(&stats->ms_d2h, s->ev[EV_SCORE1], s->ev[EV_D2H1]);
       }
       stats->gpu_launches = s->last_launches;
-      stats->fused_kernel = s->last_fused ? 1u : 0u;
+      stats->fused_kernel = s->last_fused ? (uint32_t)s->last_form : 0u;
     }
   }
   return NH_OK;

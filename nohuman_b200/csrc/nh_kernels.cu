@@ -1105,6 +1105,9 @@ struct __align__(16) StreamWarpSmem {
 #ifndef NH_STREAM_MIN_BLOCKS
 #define NH_STREAM_MIN_BLOCKS 3
 #endif
+#ifndef NH_STREAM_PREFETCH
+#define NH_STREAM_PREFETCH 1
+#endif
 template <int W>
 __global__ void __launch_bounds__(NH_BLOCK_THREADS, NH_STREAM_MIN_BLOCKS)
 k_stream_classify(const NhDbParams db, const NhBatchPtrs b, const NhScoreParams sp) {
@@ -1317,15 +1320,21 @@ k_stream_classify(const NhDbParams db, const NhBatchPtrs b, const NhScoreParams 
       };
 
       uint32_t codes = 0, ambs = 0;
-      uint32_t w_next = my_words ? __ldg(q) : 0u; /* loaded one word ahead of its use */
+      /* words are loaded NH_STREAM_PREFETCH iterations ahead of their use: a lane's 4-byte load is
+       * its own request into a memory system kept busy by the random table reads */
+      uint32_t w_q[NH_STREAM_PREFETCH];
+#pragma unroll
+      for (int pf = 0; pf < NH_STREAM_PREFETCH; pf++) w_q[pf] = (uint32_t)pf < my_words ? __ldg(q + pf) : 0u;
       for (uint32_t base_i = 0; base_i < max_words * 4u; base_i += 4u) {
 #pragma unroll
         for (int j = 0; j < 4; j++) {
           const uint32_t i = base_i + (uint32_t)j; /* index in the word-aligned stream */
           if (j == 0) {
-            codes = nh_pack4(w_next, &ambs); /* first base in bits 7..6 */
-            const uint32_t wi = (base_i >> 2) + 1u;
-            w_next = wi < my_words ? __ldg(q + wi) : 0u;
+            codes = nh_pack4(w_q[0], &ambs); /* first base in bits 7..6 */
+#pragma unroll
+            for (int pf = 0; pf + 1 < NH_STREAM_PREFETCH; pf++) w_q[pf] = w_q[pf + 1];
+            const uint32_t wi = (base_i >> 2) + NH_STREAM_PREFETCH;
+            w_q[NH_STREAM_PREFETCH - 1] = wi < my_words ? __ldg(q + wi) : 0u;
           }
           const uint32_t cc = (codes >> (6u - 2u * (uint32_t)j)) & 3u;
           const bool inside = i >= mis && i < end_idx;
@@ -1545,7 +1554,7 @@ static size_t fused_smem_bytes(const NhDbParams &db) {
 }
 
 int nh_launch_fused(const NhDbParams &db, const NhBatchPtrs &b, const NhScoreParams &sp,
-                    uint32_t tiles_upper, int sm_count, cudaStream_t st) {
+                    uint32_t tiles_upper, int sm_count, bool short_reads, cudaStream_t st, int *form) {
   uint32_t groups = (tiles_upper + 31u) / 32u;
   uint32_t blocks = (groups + NH_WARPS_PER_BLOCK - 1) / NH_WARPS_PER_BLOCK;
   uint32_t max_grid = (uint32_t)sm_count * NH_FUSED_MIN_BLOCKS;
@@ -1564,11 +1573,17 @@ int nh_launch_fused(const NhDbParams &db, const NhBatchPtrs &b, const NhScorePar
     depth = d ? atoi(d) : NH_PROBE_DEPTH_DEFAULT;
     if (depth != 1 && depth != 2) depth = NH_PROBE_DEPTH_DEFAULT;
   }
-  static int stream = -1; /* NH_FUSED_KERNEL=stream|phased */
-  if (stream < 0) {
+  /* NH_FUSED_KERNEL=stream|phased forces one form.  By default batches of single-tile reads take
+   * the streaming form (3.13 vs 3.64 ms per 1 M 2x150 bp pairs); batches of long reads, whose
+   * lookups all have to be written out for k_score anyway, take the phased form (4.6-5.3 vs
+   * 5.3-6.0 ms per 300 Mbp of 0.5-50 kb reads). */
+  static int forced = -2;
+  if (forced == -2) {
     const char *e = getenv("NH_FUSED_KERNEL");
-    stream = e ? (strcmp(e, "stream") == 0) : NH_FUSED_STREAM_DEFAULT;
+    forced = !e ? -1 : (strcmp(e, "stream") == 0 ? 1 : 0);
   }
+  const bool stream = forced >= 0 ? forced == 1 : (NH_FUSED_STREAM_DEFAULT && short_reads);
+  if (form) *form = stream ? 2 : 1;
   if (stream) {
     const uint32_t smax = (uint32_t)sm_count * NH_STREAM_MIN_BLOCKS;
     grid = blocks < smax ? blocks : smax;

@@ -116,7 +116,7 @@ int nh_launch_plan(const NhDbParams &db, const NhBatchPtrs &b, cudaStream_t st);
 /* fused path: lane-serial minimizer scan -> probe -> in-warp scoring of short units */
 bool nh_fused_supported(const NhDbParams &db);
 int nh_launch_fused(const NhDbParams &db, const NhBatchPtrs &b, const NhScoreParams &sp,
-                    uint32_t tiles_upper, int sm_count, cudaStream_t st);
+                    uint32_t tiles_upper, int sm_count, bool short_reads, cudaStream_t st, int *form);
 int nh_launch_minimizers(const NhDbParams &db, const NhBatchPtrs &b, uint32_t tiles_upper,
                          int sm_count, cudaStream_t st);
 int nh_launch_probe(const NhDbParams &db, const uint64_t *keys, uint32_t *taxa,
