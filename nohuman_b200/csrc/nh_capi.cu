@@ -486,6 +486,8 @@ extern "C" int nh_session_create(nh_db *db, const nh_params_t *params, nh_sessio
     const char *legacy = getenv("NH_LEGACY_KERNELS");
     s->use_fused = nh_fused_supported(db->params) && !(legacy && legacy[0] == '1');
     /* NH_TEST_LANE_TAXA=n shrinks the in-warp taxon table so tests reach the overflow pass */
+    const char *form = getenv("NH_FUSED_KERNEL");
+    s->fused_form = form && !strcmp(form, "phased") ? 1 : 2;
     const char *lt = getenv("NH_TEST_LANE_TAXA");
     int v = lt ? atoi(lt) : NH_LANE_TAXA;
     s->lane_taxa = v < 1 ? 1 : (v > NH_LANE_TAXA ? NH_LANE_TAXA : v);
@@ -526,6 +528,10 @@ extern "C" int nh_session_create(nh_db *db, const nh_params_t *params, nh_sessio
   ALLOC(s->d_overflow, ms);
   ALLOC(s->d_deferred, ms);
   ALLOC(s->d_counters, 1);
+  if (s->use_fused && s->fused_form == 2) {
+    ALLOC(s->d_tile_tab, s->cap_tiles);
+    ALLOC(s->d_tile_sum, s->cap_tiles);
+  }
   if (params->emit_runs) {
     ALLOC(s->d_run_ext, s->cap_lookups);
     ALLOC(s->d_run_len, s->cap_lookups);
@@ -569,6 +575,8 @@ extern "C" void nh_session_destroy(nh_session *s) {
   cudaFree(s->d_overflow);
   cudaFree(s->d_deferred);
   cudaFree(s->d_counters);
+  cudaFree(s->d_tile_tab);
+  cudaFree(s->d_tile_sum);
   cudaFree(s->d_run_ext);
   cudaFree(s->d_run_len);
   cudaFree(s->d_tile_run_off);
@@ -646,9 +654,13 @@ static int enqueue_batch(nh_session *s, const uint8_t *d_bases, const uint64_t *
   cudaEventRecord(s->ev[EV_MIN0], st);
   if (fused) {
     /* scan + probe + in-warp scoring of short units in one kernel; ms_probe reads 0 */
-    /* mean sequence length decides the form of the fused kernel: single-tile reads stream */
-    const bool short_reads = total_bases <= n_seqs * (uint64_t)(P.tile_pos + P.k - 1);
-    launches += nh_launch_fused(P, B, SP, (uint32_t)tiles_upper, sm, short_reads, st, &s->last_form);
+    /* NH_FUSED_KERNEL=stream|phased picks the form of the fused kernel (default: streaming) */
+    s->last_form = s->fused_form;
+    if (s->last_form == 2) {
+      B.tile_tab = s->d_tile_tab;
+      B.tile_sum = s->d_tile_sum;
+    }
+    launches += nh_launch_fused(P, B, SP, (uint32_t)tiles_upper, sm, s->last_form, st);
     cudaEventRecord(s->ev[EV_PROBE0], st);
   } else {
     launches += nh_launch_minimizers(P, B, (uint32_t)tiles_upper, sm, st);

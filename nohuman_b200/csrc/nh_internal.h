@@ -60,7 +60,9 @@ struct nh_session {
   uint64_t last_seqs = 0;
   bool use_fused = false, last_fused = false;
   int lane_taxa = NH_LANE_TAXA;
-  int last_form = 0; /* 1: k_scan_probe_score, 2: k_stream_classify */
+  int last_form = 0, fused_form = 2; /* 1: k_scan_probe_score, 2: k_stream_classify */
+  NhTileTab *d_tile_tab = nullptr;
+  NhTileSum *d_tile_sum = nullptr;
   NhCounters *d_counters = nullptr;
   NhCounters *h_counters = nullptr; /* pinned */
   cudaStream_t stream = nullptr;

@@ -483,6 +483,41 @@ __device__ bool score_unit(const NhDbParams &db, const NhBatchPtrs &b, const NhS
     const uint64_t len = b.offsets[s + 1] - b.offsets[s];
     if (len >= (uint64_t)db.k) total_kmers += (uint32_t)(len - (uint64_t)db.k + 1);
     const uint32_t t0 = b.tile_base[s], t1 = b.tile_base[s + 1];
+    if (b.tile_tab != nullptr && !reprobe) {
+      /* streaming kernel: every tile left its own small table; lanes take tiles in parallel */
+      bool any_ovf = false;
+      for (uint32_t tile = t0 + lane; tile < t1; tile += 32u) {
+        const NhTileSum ts = b.tile_sum[tile];
+        groups += (int)ts.groups;
+        if (ts.flags & NH_TILE_OVERFLOW) {
+          any_ovf = true;
+        } else {
+          const NhTileTab tt = b.tile_tab[tile];
+#pragma unroll
+          for (int j = 0; j < NH_LANE_TAXA; j++)
+            if (tt.keys[j]) ok &= hc_add(keys, cnts, cap_mask, tt.keys[j], tt.cnts[j]);
+        }
+        /* a tile starts with a fresh lookup even when its first minimizer equals the last one of
+         * the tile before: upstream counts that as one group */
+        if (tile > t0 && (ts.flags & NH_TILE_HAS) && (ts.flags & NH_TILE_FIRST_HIT)) {
+          uint32_t p = tile;
+          while (p > t0 && !(b.tile_sum[p - 1u].flags & NH_TILE_HAS)) p--;
+          if (p > t0 && b.tile_sum[p - 1u].last_min == ts.first_min) groups--;
+        }
+      }
+      if (__any_sync(FULL_MASK, any_ovf)) {
+        /* rare: tiles whose table overflowed kept their lookups; count them with fresh probes */
+        for (uint32_t tile = t0; tile < t1; tile++) {
+          if (!(b.tile_sum[tile].flags & NH_TILE_OVERFLOW)) continue;
+          const NhTileOut to = b.tile_out[tile];
+          for (uint32_t j = lane; j < to.lk_cnt; j += 32u) {
+            const uint32_t tx = cht_get(db, b.lk_min[to.lk_off + j]);
+            if (tx) ok &= hc_add(keys, cnts, cap_mask, tx, b.lk_cnt[to.lk_off + j]);
+          }
+        }
+      }
+      continue;
+    }
     uint64_t prev_last = NH_NONE64; /* ClassifySequence resets last_minimizer per mate */
     for (uint32_t tile = t0; tile < t1; tile++) {
       const NhTileOut to = b.tile_out[tile];
@@ -1085,16 +1120,18 @@ k_scan_probe_score(const NhDbParams db, const NhBatchPtrs b, const NhScoreParams
 struct __align__(16) StreamWarpSmem {
   uint64_t pq_key[128];                  /* closed runs waiting to be probed (ring) */
   uint32_t pq_slot[128];
-  uint16_t pq_meta[128];                 /* owner lane | k-mer count << 5 */
+  uint16_t pq_meta[128];                 /* owner lane | k-mer count << 5 | first lookup of its tile << 13 */
   uint32_t q_unit[64];                   /* probe chains that continue into the next sector */
   uint32_t q_ckey[64];
   uint32_t q_slot[64];
-  uint32_t q_aux[64];                    /* owner lane | k-mer count << 5 | sectors visited << 13 */
+  uint32_t q_aux[64];                    /* owner lane | k-mer count << 5 | first << 13 | sectors visited << 14 */
+  uint64_t first_min[32], last_min[32];  /* first / last distinct minimizer of each lane's tile */
   uint32_t keys[NH_LANE_TAXA * 32];      /* taxon tables, [slot][owner lane] */
   uint32_t cnts[NH_LANE_TAXA * 32];
   uint32_t groups[32];                   /* minimizer_hit_groups per owner lane */
-  uint8_t meta[32];                      /* per tile: owner lane | NH_META_DEFERRED */
+  uint8_t meta[32];                      /* per tile: owner lane (the lane before, for a second mate) */
   uint32_t overflow;                     /* bit per owner lane: table overflowed */
+  uint32_t first_hit;                    /* bit per lane: the tile's first lookup hit */
 };
 
 #define NH_AUX_NONE 0xFFFFFFFFu
@@ -1131,7 +1168,7 @@ k_stream_classify(const NhDbParams db, const NhBatchPtrs b, const NhScoreParams 
   const uint32_t rc_shift = 2u * (uint32_t)(l - 1);
   const uint64_t n_sectors = (db.capacity + 7ULL) >> 3;
   /* probe-chain guard for a table without any empty cell (never a real database) */
-  const uint32_t max_visits = n_sectors + 1ULL < 0x7FFFFULL ? (uint32_t)(n_sectors + 1ULL) : 0x7FFFFu;
+  const uint32_t max_visits = n_sectors + 1ULL < 0x3FFFFULL ? (uint32_t)(n_sectors + 1ULL) : 0x3FFFFu;
   uint32_t tot_lookups = 0, tot_classified = 0, tot_kept = 0;
 
   for (uint32_t group = blockIdx.x * NH_WARPS_PER_BLOCK + warp; group * 32u < n_tiles;
@@ -1147,11 +1184,15 @@ k_stream_classify(const NhDbParams db, const NhBatchPtrs b, const NhScoreParams 
       sm.cnts[i * 32 + lane] = 0;
     }
     sm.groups[lane] = 0;
-    if (lane == 0) sm.overflow = 0;
-    sm.meta[lane] = (uint8_t)(t.role == NH_ROLE_DEFERRED ? NH_META_DEFERRED
-                              : (t.role == NH_ROLE_PARTNER ? lane - 1u : lane));
-    /* lookups of this tile that other kernels read later go to global memory as well */
-    const bool spill_runs = t.role == NH_ROLE_DEFERRED || b.emit_all_taxa;
+    if (lane == 0) {
+      sm.overflow = 0;
+      sm.first_hit = 0;
+    }
+    /* every tile folds its hits into a table: a second mate into its leader's, all others into
+     * their own (tiles of deferred units hand theirs to k_score through tile_tab) */
+    sm.meta[lane] = (uint8_t)(t.role == NH_ROLE_PARTNER ? lane - 1u : lane);
+    /* the per-read output needs every lookup in global memory */
+    const bool spill_runs = b.emit_all_taxa != 0;
     __syncwarp();
 
     /* warp-uniform queue state */
@@ -1183,11 +1224,11 @@ k_stream_classify(const NhDbParams db, const NhBatchPtrs b, const NhScoreParams 
             done = true;
             result = (uint32_t)state;
           } else {
-            const uint32_t visits = (f_aux >> 13) + 1u;
+            const uint32_t visits = (f_aux >> 14) + 1u;
             if (visits >= max_visits) {
               done = true; /* went round a table without an empty cell */
             } else {
-              f_aux = (f_aux & 0x1FFFu) | (visits << 13);
+              f_aux = (f_aux & 0x3FFFu) | (visits << 14);
               f_unit = (uint64_t)f_unit + 1ULL >= n_sectors ? 0u : f_unit + 1u;
             }
           }
@@ -1204,11 +1245,11 @@ k_stream_classify(const NhDbParams db, const NhBatchPtrs b, const NhScoreParams 
         cq_n += __popc(cmask);
         if (active && done) {
           const uint32_t own_lane = f_aux & 31u;
-          const uint32_t mt = sm.meta[own_lane];
-          if ((mt & NH_META_DEFERRED) || b.emit_all_taxa) b.lk_taxon[f_slot] = result;
-          if (!(mt & NH_META_DEFERRED) && result) {
-            const uint32_t own = mt;
+          if (b.emit_all_taxa) b.lk_taxon[f_slot] = result;
+          if (result) {
+            const uint32_t own = sm.meta[own_lane];
             const uint32_t n = (f_aux >> 5) & 0xFFu;
+            if (f_aux & 0x2000u) atomicOr(&sm.first_hit, 1u << own_lane);
             atomicAdd(&sm.groups[own], 1u);
             int i = 0;
             for (; i < sp.lane_taxa; i++) {
@@ -1242,7 +1283,7 @@ k_stream_classify(const NhDbParams db, const NhBatchPtrs b, const NhScoreParams 
         const uint32_t meta = sm.pq_meta[i];
         if (db.min_hash && h < db.min_hash) {
           /* below minimum_acceptable_hash_value: kraken2 skips the lookup, taxon 0 */
-          if ((sm.meta[meta & 31u] & NH_META_DEFERRED) || b.emit_all_taxa) b.lk_taxon[f_slot] = 0u;
+          if (b.emit_all_taxa) b.lk_taxon[f_slot] = 0u;
         } else {
           const uint64_t idx = nh_fastmod(h, db.capacity, db.mod_m, db.mod_sh1, db.mod_sh2);
           f_unit = (uint32_t)(idx >> 3);
@@ -1306,11 +1347,13 @@ k_stream_classify(const NhDbParams db, const NhBatchPtrs b, const NhScoreParams 
             const uint32_t i = (pq_head + pq_n + __popc(emask & lane_lt)) & 127u;
             sm.pq_key[i] = key;
             sm.pq_slot[i] = slot;
-            sm.pq_meta[i] = (uint16_t)(lane | (count << 5));
+            sm.pq_meta[i] = (uint16_t)(lane | (count << 5) | (n_runs == 0u ? 0x2000u : 0u));
           }
           pq_n += __popc(emask);
         }
         if (pred) {
+          if (n_runs == 0u) sm.first_min[lane] = key;
+          sm.last_min[lane] = key;
           if (spill) {
             b.lk_min[slot] = key;
             b.lk_cnt[slot] = (uint8_t)count;
@@ -1394,8 +1437,28 @@ k_stream_classify(const NhDbParams db, const NhBatchPtrs b, const NhScoreParams 
       while (pq_n + cq_n != 0u || any_inflight) probe_round();
       const uint32_t ov = sm.overflow; /* final: every fold happened before the last __syncwarp */
       if (ov == 0u) break;
-      redo_lane = have && ((t.role == NH_ROLE_PARTNER ? (ov >> (lane - 1u)) : (ov >> lane)) & 1u) &&
-                  t.role != NH_ROLE_DEFERRED && !spill_runs;
+      redo_lane = have && ((t.role == NH_ROLE_PARTNER ? (ov >> (lane - 1u)) : (ov >> lane)) & 1u) && !spill_runs;
+    }
+
+    /* ---------------- tiles of deferred units: hand the tile's table to k_score ---------------- */
+    if (have && t.role == NH_ROLE_DEFERRED) {
+      const bool ovf = (sm.overflow >> lane) & 1u;
+      NhTileSum ts;
+      ts.first_min = n_runs ? sm.first_min[lane] : NH_NONE64;
+      ts.last_min = n_runs ? sm.last_min[lane] : NH_NONE64;
+      ts.groups = sm.groups[lane];
+      ts.flags = (n_runs ? NH_TILE_HAS : 0u) | (((sm.first_hit >> lane) & 1u) ? NH_TILE_FIRST_HIT : 0u) |
+                 (ovf ? NH_TILE_OVERFLOW : 0u);
+      b.tile_sum[tile] = ts;
+      if (!ovf) {
+        NhTileTab tt;
+#pragma unroll
+        for (int i = 0; i < NH_LANE_TAXA; i++) {
+          tt.keys[i] = sm.keys[i * 32 + lane];
+          tt.cnts[i] = sm.cnts[i * 32 + lane];
+        }
+        b.tile_tab[tile] = tt;
+      }
     }
 
     /* ---------------- score short units in the warp ---------------- */
@@ -1554,7 +1617,7 @@ static size_t fused_smem_bytes(const NhDbParams &db) {
 }
 
 int nh_launch_fused(const NhDbParams &db, const NhBatchPtrs &b, const NhScoreParams &sp,
-                    uint32_t tiles_upper, int sm_count, bool short_reads, cudaStream_t st, int *form) {
+                    uint32_t tiles_upper, int sm_count, int form, cudaStream_t st) {
   uint32_t groups = (tiles_upper + 31u) / 32u;
   uint32_t blocks = (groups + NH_WARPS_PER_BLOCK - 1) / NH_WARPS_PER_BLOCK;
   uint32_t max_grid = (uint32_t)sm_count * NH_FUSED_MIN_BLOCKS;
@@ -1573,17 +1636,7 @@ int nh_launch_fused(const NhDbParams &db, const NhBatchPtrs &b, const NhScorePar
     depth = d ? atoi(d) : NH_PROBE_DEPTH_DEFAULT;
     if (depth != 1 && depth != 2) depth = NH_PROBE_DEPTH_DEFAULT;
   }
-  /* NH_FUSED_KERNEL=stream|phased forces one form.  By default batches of single-tile reads take
-   * the streaming form (3.13 vs 3.64 ms per 1 M 2x150 bp pairs); batches of long reads, whose
-   * lookups all have to be written out for k_score anyway, take the phased form (4.6-5.3 vs
-   * 5.3-6.0 ms per 300 Mbp of 0.5-50 kb reads). */
-  static int forced = -2;
-  if (forced == -2) {
-    const char *e = getenv("NH_FUSED_KERNEL");
-    forced = !e ? -1 : (strcmp(e, "stream") == 0 ? 1 : 0);
-  }
-  const bool stream = forced >= 0 ? forced == 1 : (NH_FUSED_STREAM_DEFAULT && short_reads);
-  if (form) *form = stream ? 2 : 1;
+  const bool stream = form == 2;
   if (stream) {
     const uint32_t smax = (uint32_t)sm_count * NH_STREAM_MIN_BLOCKS;
     grid = blocks < smax ? blocks : smax;

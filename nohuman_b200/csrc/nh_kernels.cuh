@@ -61,6 +61,22 @@ struct NhTileOut {
   uint32_t lk_cnt; /* number of lookups (distinct-consecutive minimizers) */
 };
 
+/* What the streaming kernel leaves behind for a tile of a deferred (multi-tile) unit instead of
+ * its individual lookups: the tile's own taxon -> k-mer count table and what k_score needs to
+ * stitch tiles together. */
+struct __align__(16) NhTileTab {
+  uint32_t keys[NH_LANE_TAXA]; /* internal taxids, 0-terminated */
+  uint32_t cnts[NH_LANE_TAXA];
+};
+struct __align__(8) NhTileSum {
+  uint64_t first_min, last_min; /* first / last distinct minimizer of the tile */
+  uint32_t groups;              /* lookups of the tile that hit */
+  uint32_t flags;               /* NH_TILE_* */
+};
+#define NH_TILE_HAS 1u       /* the tile has at least one lookup */
+#define NH_TILE_FIRST_HIT 2u /* its first lookup hit (needed for the group count across tile borders) */
+#define NH_TILE_OVERFLOW 4u  /* more distinct taxa than the table holds: lk_min / lk_cnt were written instead */
+
 /* Device-side counters of one batch. */
 struct NhCounters {
   uint32_t n_tiles;
@@ -97,6 +113,8 @@ struct NhBatchPtrs {
   uint32_t *overflow_units;
   uint32_t *deferred_units; /* null: k_score walks every unit (legacy path) */
   int32_t emit_all_taxa;    /* fused kernel: store lk_taxon for every tile (per-read output wanted) */
+  NhTileTab *tile_tab;      /* streaming kernel: per-tile tables of deferred units (null: lookups in lk_*) */
+  NhTileSum *tile_sum;
   NhCounters *counters;
   /* per-position debug output of the minimizer kernel (may be null) */
   const uint64_t *dbg_pos_offsets;
@@ -116,7 +134,7 @@ int nh_launch_plan(const NhDbParams &db, const NhBatchPtrs &b, cudaStream_t st);
 /* fused path: lane-serial minimizer scan -> probe -> in-warp scoring of short units */
 bool nh_fused_supported(const NhDbParams &db);
 int nh_launch_fused(const NhDbParams &db, const NhBatchPtrs &b, const NhScoreParams &sp,
-                    uint32_t tiles_upper, int sm_count, bool short_reads, cudaStream_t st, int *form);
+                    uint32_t tiles_upper, int sm_count, int form /* 1 phased, 2 streaming */, cudaStream_t st);
 int nh_launch_minimizers(const NhDbParams &db, const NhBatchPtrs &b, uint32_t tiles_upper,
                          int sm_count, cudaStream_t st);
 int nh_launch_probe(const NhDbParams &db, const uint64_t *keys, uint32_t *taxa,
