@@ -123,6 +123,7 @@ k_plan_scan(uint64_t *__restrict__ block_sums, uint32_t nb, NhCounters *__restri
     counters->n_overflow = 0;
     counters->error = 0;
     counters->n_deferred = 0;
+    counters->next_group = 0;
   }
 }
 
@@ -1145,7 +1146,7 @@ struct __align__(16) StreamWarpSmem {
 #ifndef NH_STREAM_PREFETCH
 #define NH_STREAM_PREFETCH 1
 #endif
-template <int W>
+template <int W, bool DBG>
 __global__ void __launch_bounds__(NH_BLOCK_THREADS, NH_STREAM_MIN_BLOCKS)
 k_stream_classify(const NhDbParams db, const NhBatchPtrs b, const NhScoreParams sp) {
   static_assert(W == 5, "the scan consumes one 4-byte word per ring rotation");
@@ -1171,8 +1172,12 @@ k_stream_classify(const NhDbParams db, const NhBatchPtrs b, const NhScoreParams 
   const uint32_t max_visits = n_sectors + 1ULL < 0x3FFFFULL ? (uint32_t)(n_sectors + 1ULL) : 0x3FFFFu;
   uint32_t tot_lookups = 0, tot_classified = 0, tot_kept = 0;
 
-  for (uint32_t group = blockIdx.x * NH_WARPS_PER_BLOCK + warp; group * 32u < n_tiles;
-       group += gridDim.x * NH_WARPS_PER_BLOCK) {
+  /* groups of 32 tiles are handed out through a counter: warps that draw short tiles take more */
+  for (;;) {
+    uint32_t group = 0;
+    if (lane == 0) group = atomicAdd(&b.counters->next_group, 1u);
+    group = __shfl_sync(FULL_MASK, group, 0);
+    if ((uint64_t)group * 32ULL >= n_tiles) break;
     const uint32_t tile = group * 32u + lane;
     const bool have = tile < n_tiles;
     NhTile t;
@@ -1333,7 +1338,7 @@ k_stream_classify(const NhDbParams db, const NhBatchPtrs b, const NhScoreParams 
       uint32_t c_run = 0;           /* consecutive unambiguous bases ending here */
       uint64_t last = NH_NONE64;    /* minimizer of the open run */
       uint32_t cnt = 0;             /* k-mer positions in the open run */
-      const bool dbg = b.dbg_pos_min != nullptr && !rescan;
+      const bool dbg = DBG && !rescan; /* per-position output for nh_debug_minimizers */
       const uint64_t dbg_base = dbg && scanning ? b.dbg_pos_offsets[t.seq] + t.pos_begin : 0;
       const uint32_t first_pos = mis + (uint32_t)(k - 1);
       const uint32_t end_idx = mis + nb;
@@ -1581,8 +1586,10 @@ cudaError_t nh_kernels_init(void) {
                            NH_SMEM_PARENT_MAX * 4 + NH_WARPS_PER_BLOCK * NH_WARP_HASH_SLOTS * 8);
   if (e != cudaSuccess) return e;
   const int fused_max = NH_SMEM_PARENT_MAX * 4 + NH_WARPS_PER_BLOCK * (int)sizeof(FusedWarpSmem);
-  e = cudaFuncSetAttribute(k_stream_classify<5>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           NH_SMEM_PARENT_MAX * 4 + NH_WARPS_PER_BLOCK * (int)sizeof(StreamWarpSmem));
+  const int stream_max = NH_SMEM_PARENT_MAX * 4 + NH_WARPS_PER_BLOCK * (int)sizeof(StreamWarpSmem);
+  e = cudaFuncSetAttribute(k_stream_classify<5, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, stream_max);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(k_stream_classify<5, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, stream_max);
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(k_scan_probe_score<5, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused_max);
   if (e != cudaSuccess) return e;
@@ -1643,7 +1650,10 @@ int nh_launch_fused(const NhDbParams &db, const NhBatchPtrs &b, const NhScorePar
     if (grid == 0) grid = 1;
     const uint32_t parent_words = db.node_count <= NH_SMEM_PARENT_MAX ? db.node_count : 0u;
     const size_t ssmem = (size_t)((parent_words + 3u) & ~3u) * 4 + NH_WARPS_PER_BLOCK * sizeof(StreamWarpSmem);
-    k_stream_classify<5><<<grid, NH_BLOCK_THREADS, ssmem, st>>>(db, b, sp);
+    if (b.dbg_pos_min != nullptr)
+      k_stream_classify<5, true><<<grid, NH_BLOCK_THREADS, ssmem, st>>>(db, b, sp);
+    else
+      k_stream_classify<5, false><<<grid, NH_BLOCK_THREADS, ssmem, st>>>(db, b, sp);
     return 1;
   }
   const size_t smem = fused_smem_bytes(db);

@@ -86,7 +86,7 @@ struct NhCounters {
   uint32_t n_overflow;   /* units sent to the big-table scoring pass */
   uint32_t error;        /* nonzero: a unit exceeded even the big table */
   uint32_t n_deferred;   /* units k_score handles (not scored inside the fused kernel) */
-  uint32_t pad[1];
+  uint32_t next_group;   /* streaming kernel: next group of 32 tiles to hand out */
 };
 
 struct NhBatchPtrs {
