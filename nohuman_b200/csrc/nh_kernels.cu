@@ -1,19 +1,24 @@
 /*
- * nh_kernels.cu — the four classification stages as hand-written sm_100a
- * kernels.  Integer/byte work bound by issue slots (minimizers) and by
- * random 32-byte HBM sector reads (hash probe); no tensor-core work exists
- * on this path.
+ * nh_kernels.cu — the classification path as hand-written sm_100a kernels.
+ * Integer/byte work bound by issue slots (minimizer scan) and by random
+ * 32-byte reads of the hash table, which on B200 are limited by address
+ * translation; no tensor-core work exists on this path.
  *
  * Upstream units each kernel stands for (kraken2 @ reference Dockerfile:15,
  * 35-38; behavioural spec SURVEY.md Appendix A):
- *   k_plan_*        (none: work decomposition into <=124-position tiles)
- *   k_minimizers    mmscanner.cc MinimizerScanner::NextMinimizer/is_ambiguous
- *                   + the last_minimizer de-duplication of classify.cc
- *                   ClassifySequence                                   (A.3, A.5)
- *   k_probe         compact_hash.cc CompactHashTable::Get + kv_store.h
- *                   MurmurHash3 (LINEAR_PROBING build)                 (A.4)
- *   k_score         classify.cc ClassifySequence tail + ResolveTree,
- *                   taxonomy.cc IsAAncestorOfB / LowestCommonAncestor  (A.5)
+ *   k_plan_*             (none: tiles, lookup slots, tile roles, deferred units)
+ *   k_stream_classify    mmscanner.cc MinimizerScanner::NextMinimizer/is_ambiguous,
+ *                        the last_minimizer de-duplication of classify.cc
+ *                        ClassifySequence, kv_store.h MurmurHash3, compact_hash.cc
+ *                        CompactHashTable::Get (LINEAR_PROBING build), classify.cc
+ *                        ResolveTree + taxonomy.cc IsAAncestorOfB /
+ *                        LowestCommonAncestor — one kernel, the default path (A.3-A.5)
+ *   k_scan_probe_score   the same work in three phases (NH_FUSED_KERNEL=phased)
+ *   k_score, k_score_big ClassifySequence tail + ResolveTree for multi-tile units
+ *                        (long reads) and units with many distinct taxa         (A.5)
+ *   k_minimizers, k_probe  warp-per-tile scan and thread-per-lookup probe: any window
+ *                        width k-l+1 <= 32, the synthetic builder, A/B runs     (A.3, A.4)
+ *   k_gather_runs        per-read hit runs for kraken2's --output lines          (A.6)
  * and, in the reference itself, the keep/drop polarity of
  * src/main.rs:259-265 (--classified-out vs --unclassified-out).
  */
@@ -1146,7 +1151,7 @@ struct __align__(16) StreamWarpSmem {
 #ifndef NH_STREAM_PREFETCH
 #define NH_STREAM_PREFETCH 1
 #endif
-template <int W, bool DBG>
+template <int W, bool DBG, bool REV0>
 __global__ void __launch_bounds__(NH_BLOCK_THREADS, NH_STREAM_MIN_BLOCKS)
 k_stream_classify(const NhDbParams db, const NhBatchPtrs b, const NhScoreParams sp) {
   static_assert(W == 5, "the scan consumes one 4-byte word per ring rotation");
@@ -1167,9 +1172,12 @@ k_stream_classify(const NhDbParams db, const NhBatchPtrs b, const NhScoreParams 
   const int k = db.k, l = db.l;
   const uint64_t lmask = (1ULL << (2 * l)) - 1ULL;
   const uint32_t rc_shift = 2u * (uint32_t)(l - 1);
-  const uint64_t n_sectors = (db.capacity + 7ULL) >> 3;
+  const uint32_t n_sectors = (uint32_t)((db.capacity + 7ULL) >> 3); /* nh_fused_supported: capacity < 2^35 */
+  const uint32_t last_sector = n_sectors - 1u;
+  /* cells of the last sector that exist (the allocation is zero-padded past the table's end) */
+  const uint32_t last_range = (db.capacity & 7ULL) ? (1u << (uint32_t)(db.capacity & 7ULL)) - 1u : 0xFFu;
   /* probe-chain guard for a table without any empty cell (never a real database) */
-  const uint32_t max_visits = n_sectors + 1ULL < 0x3FFFFULL ? (uint32_t)(n_sectors + 1ULL) : 0x3FFFFu;
+  const uint32_t max_visits = n_sectors + 1u < 0x3FFFFu ? n_sectors + 1u : 0x3FFFFu;
   uint32_t tot_lookups = 0, tot_classified = 0, tot_kept = 0;
 
   /* groups of 32 tiles are handed out through a counter: warps that draw short tiles take more */
@@ -1215,9 +1223,8 @@ k_stream_classify(const NhDbParams db, const NhBatchPtrs b, const NhScoreParams 
         bool done = false;
         uint32_t result = 0;
         if (active) {
-          const uint64_t cell0 = (uint64_t)f_unit * 8ULL;
           uint32_t range = 0xFFu << f_start;
-          if (cell0 + 8ULL > db.capacity) range &= (1u << (uint32_t)(db.capacity - cell0)) - 1u;
+          if (f_unit == last_sector) range &= last_range;
           int state = -1;
 #pragma unroll
           for (int j = 7; j >= 0; j--) {
@@ -1234,7 +1241,7 @@ k_stream_classify(const NhDbParams db, const NhBatchPtrs b, const NhScoreParams 
               done = true; /* went round a table without an empty cell */
             } else {
               f_aux = (f_aux & 0x3FFFu) | (visits << 14);
-              f_unit = (uint64_t)f_unit + 1ULL >= n_sectors ? 0u : f_unit + 1u;
+              f_unit = f_unit == last_sector ? 0u : f_unit + 1u;
             }
           }
         }
@@ -1332,9 +1339,12 @@ k_stream_classify(const NhDbParams db, const NhBatchPtrs b, const NhScoreParams 
       const uint32_t max_words = __reduce_max_sync(FULL_MASK, my_words);
 
       uint64_t fwd = 0, rc = 0;
-      uint64_t ring[4];
+      /* window of 5 candidates c_i..c_{i-4}: a_i = min(c_i, c_{i-1}), m_i = min(a_i, a_{i-2}, c_{i-4});
+       * ring[] holds c_{i-1}..c_{i-4}, pair[] holds a_{i-1}, a_{i-2} */
+      uint64_t ring[4], pair[2];
 #pragma unroll
       for (int i = 0; i < 4; i++) ring[i] = NH_NONE64;
+      pair[0] = pair[1] = NH_NONE64;
       uint32_t c_run = 0;           /* consecutive unambiguous bases ending here */
       uint64_t last = NH_NONE64;    /* minimizer of the open run */
       uint32_t cnt = 0;             /* k-mer positions in the open run */
@@ -1393,14 +1403,15 @@ k_stream_classify(const NhDbParams db, const NhBatchPtrs b, const NhScoreParams 
           c_run = amb ? 0u : c_run + 1u;
           uint64_t cand = NH_NONE64;
           if (c_run >= (uint32_t)l) {
-            const uint64_t rcv = db.revcom_version == 0
-                                     ? (((rc << (64 - 2 * l)) | ((1ULL << (64 - 2 * l)) - 1ULL)) & lmask)
-                                     : rc;
+            /* revcom_version 0 (databases built before kraken2 2.0.8) keeps the un-shifted low bits */
+            const bool rev0 = REV0 || (DBG && db.revcom_version == 0); /* the debug instantiation decides at run time */
+            const uint64_t rcv = rev0 ? (((rc << (64 - 2 * l)) | ((1ULL << (64 - 2 * l)) - 1ULL)) & lmask) : rc;
             cand = ((fwd < rcv ? fwd : rcv) & db.seed_mask) ^ db.toggle;
           }
-          uint64_t m = cand;
-#pragma unroll
-          for (int r = 0; r < 4; r++) m = min_u64(m, ring[r]);
+          const uint64_t a_i = min_u64(cand, ring[0]);
+          const uint64_t m = min_u64(min_u64(a_i, pair[1]), ring[3]);
+          pair[1] = pair[0];
+          pair[0] = a_i;
 #pragma unroll
           for (int r = 3; r > 0; r--) ring[r] = ring[r - 1];
           ring[0] = cand;
@@ -1587,9 +1598,11 @@ cudaError_t nh_kernels_init(void) {
   if (e != cudaSuccess) return e;
   const int fused_max = NH_SMEM_PARENT_MAX * 4 + NH_WARPS_PER_BLOCK * (int)sizeof(FusedWarpSmem);
   const int stream_max = NH_SMEM_PARENT_MAX * 4 + NH_WARPS_PER_BLOCK * (int)sizeof(StreamWarpSmem);
-  e = cudaFuncSetAttribute(k_stream_classify<5, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, stream_max);
+  e = cudaFuncSetAttribute(k_stream_classify<5, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, stream_max);
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(k_stream_classify<5, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, stream_max);
+  e = cudaFuncSetAttribute(k_stream_classify<5, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, stream_max);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(k_stream_classify<5, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, stream_max);
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(k_scan_probe_score<5, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused_max);
   if (e != cudaSuccess) return e;
@@ -1650,10 +1663,12 @@ int nh_launch_fused(const NhDbParams &db, const NhBatchPtrs &b, const NhScorePar
     if (grid == 0) grid = 1;
     const uint32_t parent_words = db.node_count <= NH_SMEM_PARENT_MAX ? db.node_count : 0u;
     const size_t ssmem = (size_t)((parent_words + 3u) & ~3u) * 4 + NH_WARPS_PER_BLOCK * sizeof(StreamWarpSmem);
-    if (b.dbg_pos_min != nullptr)
-      k_stream_classify<5, true><<<grid, NH_BLOCK_THREADS, ssmem, st>>>(db, b, sp);
+    if (b.dbg_pos_min != nullptr) /* nh_debug_minimizers */
+      k_stream_classify<5, true, false><<<grid, NH_BLOCK_THREADS, ssmem, st>>>(db, b, sp);
+    else if (db.revcom_version == 0)
+      k_stream_classify<5, false, true><<<grid, NH_BLOCK_THREADS, ssmem, st>>>(db, b, sp);
     else
-      k_stream_classify<5, false><<<grid, NH_BLOCK_THREADS, ssmem, st>>>(db, b, sp);
+      k_stream_classify<5, false, false><<<grid, NH_BLOCK_THREADS, ssmem, st>>>(db, b, sp);
     return 1;
   }
   const size_t smem = fused_smem_bytes(db);
