@@ -851,9 +851,7 @@ k_scan_probe_score(const NhDbParams db, const NhBatchPtrs b, const NhScoreParams
           const bool newrun = nonamb && mz != last;
           if (newrun && cnt) {
             out_min[n_runs] = last;
-#ifndef NH_EXP_NO_CNT_STORES
             out_cnt[n_runs] = (uint8_t)cnt;
-#endif
             n_runs++;
           }
           cnt = newrun ? 1u : cnt + (nonamb ? 1u : 0u);
