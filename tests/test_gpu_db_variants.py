@@ -36,7 +36,8 @@ def check(oracle_db, path, fused_expected, paired=True, conf=0.2):
         call, keep, st = sess.classify(bases, offsets)
         icall, tk, hg = sess.debug_last_batch(len(call))
         mins, amb, pos_off = sess.debug_minimizers(bases[:int(offsets[40])], offsets[:41])
-    assert bool(st.fused_kernel) == fused_expected
+    import os
+    assert bool(st.fused_kernel) == (fused_expected and os.environ.get("NH_LEGACY_KERNELS") != "1")
     np.testing.assert_array_equal(tk, want["total_kmers"])
     np.testing.assert_array_equal(hg, want["hit_groups"])
     np.testing.assert_array_equal(icall, want["call"])
