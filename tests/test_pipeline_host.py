@@ -189,3 +189,27 @@ def test_errors(tmp_path):
     ok.write_bytes(b"@r\nACGT\n+\nIIII\n")
     with pytest.raises(NhError):
         rewrite_files(keep, call, ok, tmp_path / "o.fq", out_format="q")
+
+
+def test_unusual_but_valid_endings(tmp_path):
+    """no trailing newline, blank line at the end, a record cut off in the middle: no hang, no crash;
+    what was read completely is written (kraken2's reader stops at the first empty header line)"""
+    keep, call = np.ones(8, np.uint8), np.zeros(8, np.uint32)
+    a = tmp_path / "nonl.fq"
+    a.write_bytes(b"@r1\nACGT\n+\nIIII\n@r2\nGGCC\n+\nJJJJ")  # no final newline
+    st = rewrite_files(keep, call, a, tmp_path / "o1.fq")
+    assert st.total == 2 and open(tmp_path / "o1.fq", "rb").read() == b"@r1\nACGT\n+\nIIII\n@r2\nGGCC\n+\nJJJJ\n"
+    b = tmp_path / "blank.fq"
+    b.write_bytes(b"@r1\nACGT\n+\nIIII\n\n\n")
+    st = rewrite_files(keep, call, b, tmp_path / "o2.fq")
+    assert st.total == 1
+    c = tmp_path / "cut.fq"
+    c.write_bytes(b"@r1\nACGT\n+\nIIII\n@r2\nGG")  # truncated second record: sequence only
+    st = rewrite_files(keep, call, c, tmp_path / "o3.fq")
+    assert st.total == 2  # kraken2 also hands the partial record on; its quality string is empty
+    assert open(tmp_path / "o3.fq", "rb").read() == b"@r1\nACGT\n+\nIIII\n@r2\nGG\n+\n\n"
+    d = tmp_path / "lower.fa"
+    d.write_bytes(b">s1 desc\nacgtn\nACGT\n>s2\n\n>s3\nTT\n")
+    st = rewrite_files(keep, call, d, tmp_path / "o4.fa")
+    assert st.total == 3
+    assert open(tmp_path / "o4.fa", "rb").read() == b">s1 desc\nacgtnACGT\n>s2\n\n>s3\nTT\n"
