@@ -802,10 +802,20 @@ static int run_pipeline(const Decider &dec, const nh_files_t *files, nh_run_stat
   bool failed = false;
   std::string fail_msg;
   int live_classifiers = 0;
+  /* back-pressure: the GPU outruns the output compressor by orders of magnitude, so batches
+   * are only handed out while fewer than NH_MAX_AHEAD are waiting for the writer */
+  constexpr uint64_t NH_MAX_AHEAD = 8;
+  std::mutex ahead_m;
+  std::condition_variable ahead_cv;
+  uint64_t written_id = 0;
 
   auto take = [&]() -> std::unique_ptr<Work> {
     std::lock_guard<std::mutex> lk(pair_m);
     if (input_done) return nullptr;
+    {
+      std::unique_lock<std::mutex> al(ahead_m);
+      ahead_cv.wait(al, [&] { return next_id < written_id + NH_MAX_AHEAD; });
+    }
     auto w = std::make_unique<Work>();
     for (int f = 0; f < nf; f++) {
       std::unique_ptr<Chunk> c;
@@ -928,6 +938,11 @@ static int run_pipeline(const Decider &dec, const nh_files_t *files, nh_run_stat
       done.erase(it);
     }
     want++;
+    {
+      std::lock_guard<std::mutex> al(ahead_m);
+      written_id = want;
+      ahead_cv.notify_all();
+    }
     if (!w->error.empty()) {
       if (!failed) fail_msg = w->error;
       failed = true;
