@@ -573,6 +573,9 @@ struct Work {
   std::vector<uint8_t> keep;
   std::vector<uint32_t> first_run, run_ext; /* per-sequence hit runs (kraken output only) */
   std::vector<uint8_t> run_len;
+  std::string out[2];  /* kept records of this batch, serialised by the classifier thread */
+  std::string klines;  /* kraken2 --output lines of this batch */
+  uint64_t n_classified = 0, bases = 0;
   std::string error;
 };
 
@@ -911,6 +914,33 @@ static int run_pipeline(const Decider &dec, const nh_files_t *files, nh_run_stat
             }
           }
         }
+        if (w->error.empty() && w->n_units) {
+          /* serialise here, in parallel across batches; the writer only restores the order */
+          if (want_lines) {
+            w->klines.reserve(w->n_units * 96);
+            for (uint64_t i = 0; i < w->n_units; i++) append_kraken_line(w->klines, *w, i, nf, db_k, db_amb_span);
+          }
+          for (int f = 0; f < nf; f++) {
+            uint64_t kept_bytes = 0;
+            for (uint64_t i = 0; i < w->n_units; i++) {
+              const Rec &r = w->c[f].recs[i];
+              w->bases += r.seq_len;
+              if (w->keep[i]) kept_bytes += r.hdr_len + 2ull * r.seq_len + 32;
+            }
+            w->out[f].reserve(kept_bytes);
+          }
+          for (uint64_t i = 0; i < w->n_units; i++) {
+            const bool classified = w->call[i] != 0;
+            w->n_classified += classified;
+            if (!w->keep[i]) continue;
+            for (int f = 0; f < nf; f++)
+              append_record(w->out[f], w->c[f], w->c[f].recs[i], classified && files->tag_classified, w->call[i]);
+          }
+          for (int f = 0; f < nf; f++) { /* the text arena is no longer needed */
+            std::string().swap(w->c[f].text);
+            if (!want_report) std::vector<Rec>().swap(w->c[f].recs);
+          }
+        }
         std::lock_guard<std::mutex> lk(done_m);
         done[w->id] = std::move(w);
         done_cv.notify_all();
@@ -948,33 +978,30 @@ static int run_pipeline(const Decider &dec, const nh_files_t *files, nh_run_stat
       failed = true;
     }
     if (failed) continue; /* drain */
-    if (kout) {
-      std::string lines;
-      lines.reserve(w->n_units * 96);
-      for (uint64_t i = 0; i < w->n_units; i++) append_kraken_line(lines, *w, i, nf, db_k, db_amb_span);
-      if (fwrite(lines.data(), 1, lines.size(), kout) != lines.size()) {
-        failed = true;
-        fail_msg = std::string("writing ") + files->kraken_output + " failed";
-      }
+    if (kout && fwrite(w->klines.data(), 1, w->klines.size(), kout) != w->klines.size()) {
+      failed = true;
+      fail_msg = std::string("writing ") + files->kraken_output + " failed";
     }
     if (want_report)
       for (uint64_t i = 0; i < w->n_units; i++)
         if (w->call[i]) call_counts[ext_to_internal[w->call[i]]]++;
-    for (uint64_t i = 0; i < w->n_units; i++) {
-      const bool classified = w->call[i] != 0;
-      n_classified += classified;
-      if (!w->keep[i]) continue;
-      for (int f = 0; f < nf; f++) {
-        append_record(pend[f], w->c[f], w->c[f].recs[i], classified && files->tag_classified, w->call[i]);
+    n_classified += w->n_classified;
+    total_units += w->n_units;
+    total_bases += w->bases;
+    for (int f = 0; f < nf; f++) {
+      /* cut into compression blocks; a few bytes of one batch may ride along with the next */
+      const std::string &o = w->out[f];
+      size_t pos = 0;
+      while (pos < o.size()) {
+        const size_t take_n = std::min(o.size() - pos, NH_OUT_BLOCK - pend[f].size());
+        pend[f].append(o, pos, take_n);
+        pos += take_n;
         if (pend[f].size() >= NH_OUT_BLOCK) {
           bw.submit(f, std::move(pend[f]));
           pend[f].clear();
         }
       }
     }
-    total_units += w->n_units;
-    for (int f = 0; f < nf; f++)
-      for (uint64_t i = 0; i < w->n_units; i++) total_bases += w->c[f].recs[i].seq_len;
   }
   for (int f = 0; f < nf; f++) bw.submit(f, std::move(pend[f]));
   for (int f = 0; f < nf; f++) chunks[f].close();
