@@ -7,9 +7,9 @@
  *   reader thread per input file   inflate (zlib; bzip2 through a pipe) + FASTQ/FASTA parse
  *        |  chunks of NH_CHUNK_RECORDS records
  *   classifier threads (2 per GPU) mates interleaved into PINNED bases/offsets,
- *        |                         nh_classify_batch (H2D, kernels, D2H) on their own session
- *   writer thread                  batches back in input order, kept records re-serialised
- *        |                         the way kraken2 prints them, cut into blocks
+ *        |                         nh_classify_batch (H2D, kernels, D2H) on their own session,
+ *        |                         kept records re-serialised the way kraken2 prints them
+ *   writer thread                  batches back in input order, cut into blocks
  *   compressor pool (-t threads)   every block an independent gzip member / zstd frame
  *        |                         (what gzp does for the reference), written in order
  *   final out1 / out2              no temporary FASTQ, no second pass
