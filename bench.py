@@ -111,7 +111,7 @@ class ClockSampler:
     def stop(self):
         import datetime
         if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi not sampled on this rank"]}
         time.sleep(0.12)
         self.proc.terminate()
         try:
@@ -280,7 +280,8 @@ def main():
         return sess.sync()
 
     sampler = ClockSampler(dev)
-    sampler.start()
+    if rank == 0:  # one nvidia-smi poller per run is enough; rank 0's GPU is the one reported
+        sampler.start()
     for i in range(args.warmup):
         st = step(i)
     random_gbs = db.random_gather_gbs(1 << 27, 3) if rank == 0 else None
