@@ -116,18 +116,180 @@ static int spawn_filter(const std::vector<std::string> &argv, int stdin_fd, int 
   return rc;
 }
 
+/* ------------------------------------------------------------------ */
+/* blocked gzip (BGZF: what bgzip, bcl2fastq and this library write): every member carries its
+ * compressed size in a 'BC' extra subfield, so members can be inflated in parallel */
+
+static bool bgzf_block_size(const unsigned char *hdr, size_t n, size_t *xlen, size_t *bsize) {
+  if (n < 12 || hdr[0] != 0x1f || hdr[1] != 0x8b || hdr[2] != 8 || !(hdr[3] & 4)) return false;
+  *xlen = hdr[10] | (size_t)hdr[11] << 8;
+  if (n < 12 + *xlen) return false;
+  for (size_t o = 12; o + 4 <= 12 + *xlen;) {
+    const size_t slen = hdr[o + 2] | (size_t)hdr[o + 3] << 8;
+    if (hdr[o] == 'B' && hdr[o + 1] == 'C' && slen == 2 && o + 6 <= 12 + *xlen) {
+      *bsize = (hdr[o + 4] | (size_t)hdr[o + 5] << 8) + 1;
+      return true;
+    }
+    o += 4 + slen;
+  }
+  return false;
+}
+
+class BgzfReader {
+ public:
+  ~BgzfReader() { close(); }
+  bool open(const std::string &path, int threads) {
+    f_ = fopen(path.c_str(), "rb");
+    if (!f_) return false;
+    setvbuf(f_, nullptr, _IOFBF, 4u << 20);
+    producer_ = std::thread([this] { produce(); });
+    for (int i = 0; i < threads; i++) workers_.emplace_back([this] { work(); });
+    return true;
+  }
+  long read(char *buf, size_t n) {
+    size_t got = 0;
+    while (got < n) {
+      std::shared_ptr<Blk> b;
+      {
+        std::unique_lock<std::mutex> lk(m_);
+        cv_.wait(lk, [&] { return (!order_.empty() && order_.front()->done) || (eof_ && order_.empty()) || error_; });
+        if (error_) return -1;
+        if (order_.empty()) break;
+        b = order_.front();
+        if (!b->ok) return -1;
+      }
+      const size_t avail = b->raw.size() - off_;
+      const size_t take = avail < n - got ? avail : n - got;
+      memcpy(buf + got, b->raw.data() + off_, take);
+      got += take;
+      off_ += take;
+      if (off_ == b->raw.size()) {
+        std::lock_guard<std::mutex> lk(m_);
+        order_.pop_front();
+        off_ = 0;
+        space_.notify_all();
+      }
+    }
+    return (long)got;
+  }
+  void close() {
+    {
+      std::lock_guard<std::mutex> lk(m_);
+      stop_ = true;
+      cv_.notify_all();
+      space_.notify_all();
+    }
+    if (producer_.joinable()) producer_.join();
+    for (auto &t : workers_)
+      if (t.joinable()) t.join();
+    workers_.clear();
+    if (f_) fclose(f_), f_ = nullptr;
+  }
+
+ private:
+  struct Blk {
+    std::string comp, raw;
+    bool done = false, ok = true;
+  };
+  void produce() {
+    for (;;) {
+      unsigned char hdr[12 + 65536];
+      size_t n = fread(hdr, 1, 12, f_);
+      bool bad = false;
+      auto b = std::make_shared<Blk>();
+      if (n == 0) {
+        /* clean end of file */
+      } else {
+        size_t xlen = n == 12 ? (hdr[10] | (size_t)hdr[11] << 8) : 0, bsize = 0;
+        if (n != 12 || fread(hdr + 12, 1, xlen, f_) != xlen || !bgzf_block_size(hdr, 12 + xlen, &xlen, &bsize) ||
+            bsize < 12 + xlen + 8) {
+          bad = true;
+        } else {
+          b->comp.resize(bsize - 12 - xlen);
+          if (fread(&b->comp[0], 1, b->comp.size(), f_) != b->comp.size()) bad = true;
+        }
+      }
+      std::unique_lock<std::mutex> lk(m_);
+      if (n == 0 || bad) {
+        if (bad) error_ = true;
+        eof_ = true;
+        cv_.notify_all();
+        return;
+      }
+      space_.wait(lk, [&] { return order_.size() < 512 || stop_; });
+      if (stop_) return;
+      order_.push_back(b);
+      todo_.push_back(b);
+      cv_.notify_all();
+    }
+  }
+  void work() {
+    z_stream zs;
+    memset(&zs, 0, sizeof zs);
+    if (inflateInit2(&zs, -15) != Z_OK) return;
+    for (;;) {
+      std::shared_ptr<Blk> b;
+      {
+        std::unique_lock<std::mutex> lk(m_);
+        cv_.wait(lk, [&] { return !todo_.empty() || eof_ || stop_; });
+        if (stop_ || (todo_.empty() && eof_)) break;
+        if (todo_.empty()) continue;
+        b = todo_.front();
+        todo_.pop_front();
+      }
+      const size_t clen = b->comp.size() - 8;
+      const unsigned char *tr = (const unsigned char *)b->comp.data() + clen;
+      const uint32_t crc = tr[0] | tr[1] << 8 | tr[2] << 16 | (uint32_t)tr[3] << 24;
+      const uint32_t isize = tr[4] | tr[5] << 8 | tr[6] << 16 | (uint32_t)tr[7] << 24;
+      b->raw.resize(isize);
+      inflateReset(&zs);
+      zs.next_in = (Bytef *)b->comp.data();
+      zs.avail_in = (uInt)clen;
+      zs.next_out = (Bytef *)(isize ? &b->raw[0] : nullptr);
+      zs.avail_out = isize;
+      const int rc = isize ? inflate(&zs, Z_FINISH) : Z_STREAM_END;
+      const bool ok = rc == Z_STREAM_END && zs.total_out == isize &&
+                      (uint32_t)crc32(crc32(0L, Z_NULL, 0), (const Bytef *)b->raw.data(), isize) == crc;
+      std::string().swap(b->comp);
+      std::lock_guard<std::mutex> lk(m_);
+      b->ok = ok;
+      b->done = true;
+      cv_.notify_all();
+    }
+    inflateEnd(&zs);
+  }
+  FILE *f_ = nullptr;
+  std::thread producer_;
+  std::vector<std::thread> workers_;
+  std::mutex m_;
+  std::condition_variable cv_, space_;
+  std::deque<std::shared_ptr<Blk>> order_, todo_;
+  size_t off_ = 0;
+  bool eof_ = false, error_ = false, stop_ = false;
+};
+
 class InputStream {
  public:
   ~InputStream() { close(); }
-  bool open(const std::string &path, std::string &err) {
+  bool open(const std::string &path, int threads, std::string &err) {
     FILE *f = fopen(path.c_str(), "rb");
     if (!f) {
       err = "cannot open " + path;
       return false;
     }
-    unsigned char magic[6] = {0};
+    unsigned char magic[64] = {0};
     size_t n = fread(magic, 1, sizeof magic, f);
     fclose(f);
+    size_t xlen = 0, bsize = 0;
+    if (threads > 1 && bgzf_block_size(magic, n, &xlen, &bsize)) {
+      /* blocked gzip: members inflated in parallel */
+      bgzf_.reset(new BgzfReader());
+      if (!bgzf_->open(path, threads)) {
+        err = "cannot open " + path;
+        return false;
+      }
+      return true;
+    }
     if (n >= 3 && magic[0] == 'B' && magic[1] == 'Z' && magic[2] == 'h') {
       int fds[2];
       if (pipe2(fds, O_CLOEXEC)) {
@@ -165,6 +327,7 @@ class InputStream {
   }
   /* returns bytes read, 0 at EOF, -1 on error */
   long read(char *buf, size_t n) {
+    if (bgzf_) return bgzf_->read(buf, n);
     if (gz_) {
       int r = gzread(gz_, buf, (unsigned)n);
       return r;
@@ -177,6 +340,7 @@ class InputStream {
     return -1;
   }
   void close() {
+    bgzf_.reset();
     if (gz_) gzclose(gz_), gz_ = nullptr;
     if (pipe_) fclose(pipe_), pipe_ = nullptr;
     if (pid_ > 0) {
@@ -187,6 +351,7 @@ class InputStream {
   }
 
  private:
+  std::unique_ptr<BgzfReader> bgzf_;
   gzFile gz_ = nullptr;
   FILE *pipe_ = nullptr;
   pid_t pid_ = -1;
@@ -212,10 +377,10 @@ struct Chunk {
 
 class RecordReader {
  public:
-  bool open(const std::string &path, std::string &err) {
+  bool open(const std::string &path, int threads, std::string &err) {
     path_ = path;
     buf_.resize(4u << 20);
-    return in_.open(path, err);
+    return in_.open(path, threads, err);
   }
   /* fills `c` with up to NH_CHUNK_RECORDS records; c.last set at EOF */
   void next_chunk(Chunk &c) {
@@ -385,22 +550,45 @@ struct ZstdLib {
   }
 };
 
-static bool gzip_member(const std::string &in, std::string &out) {
+/* gzip output is written as BGZF: a series of gzip members of at most 64 KiB, each announcing its
+ * compressed size in a 'BC' extra subfield.  Any gunzip reads it as ordinary multi-member gzip (which
+ * is also what gzp writes for the reference, src/compression.rs:214-234); bgzip-aware tools and this
+ * library's own reader can inflate the members in parallel. */
+static const size_t BGZF_INPUT = 0xff00;
+static const unsigned char BGZF_EOF[28] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0,
+                                           0x1b, 0, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+
+static bool bgzf_members(const std::string &in, std::string &out) {
   z_stream zs;
   memset(&zs, 0, sizeof zs);
-  /* level 6 = the default level flate2/gzp use in the reference (src/compression.rs:214-234) */
-  if (deflateInit2(&zs, 6, Z_DEFLATED, 15 + 16, 8, Z_DEFAULT_STRATEGY) != Z_OK) return false;
-  out.resize(deflateBound(&zs, in.size()) + 32);
-  zs.next_in = (Bytef *)in.data();
-  zs.avail_in = (uInt)in.size();
-  zs.next_out = (Bytef *)&out[0];
-  zs.avail_out = (uInt)out.size();
-  int rc = deflate(&zs, Z_FINISH);
-  size_t n = zs.total_out;
+  /* level 6 = the default level flate2/gzp use in the reference */
+  if (deflateInit2(&zs, 6, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY) != Z_OK) return false;
+  out.clear();
+  out.reserve(in.size() / 3 + 1024);
+  unsigned char buf[65536];
+  bool ok = true;
+  for (size_t pos = 0; pos < in.size() && ok; pos += BGZF_INPUT) {
+    const size_t n = std::min(BGZF_INPUT, in.size() - pos);
+    deflateReset(&zs);
+    zs.next_in = (Bytef *)in.data() + pos;
+    zs.avail_in = (uInt)n;
+    zs.next_out = buf + 18;
+    zs.avail_out = sizeof buf - 18 - 8;
+    if (deflate(&zs, Z_FINISH) != Z_STREAM_END) {
+      ok = false;
+      break;
+    }
+    const size_t clen = zs.total_out, bsize = 18 + clen + 8;
+    const unsigned char hdr[18] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0,
+                                   (unsigned char)((bsize - 1) & 0xff), (unsigned char)((bsize - 1) >> 8)};
+    memcpy(buf, hdr, 18);
+    const uint32_t crc = (uint32_t)crc32(crc32(0L, Z_NULL, 0), (const Bytef *)in.data() + pos, (uInt)n);
+    unsigned char *tr = buf + 18 + clen;
+    for (int i = 0; i < 4; i++) tr[i] = (unsigned char)(crc >> (8 * i)), tr[4 + i] = (unsigned char)((uint32_t)n >> (8 * i));
+    out.append((const char *)buf, bsize);
+  }
   deflateEnd(&zs);
-  if (rc != Z_STREAM_END) return false;
-  out.resize(n);
-  return true;
+  return ok;
 }
 
 /* One output file.  Blocks are compressed by a shared pool and written in
@@ -443,7 +631,7 @@ class OutputFile {
   }
   bool parallel() const { return format_ == 'g' || format_ == 'z'; }
   bool compress_block(const std::string &in, std::string &out) {
-    if (format_ == 'g') return gzip_member(in, out);
+    if (format_ == 'g') return bgzf_members(in, out);
     if (format_ == 'z') {
       out.resize(zstd_.bound(in.size()));
       size_t n = zstd_.compress(&out[0], out.size(), in.data(), in.size(), 3);
@@ -456,7 +644,8 @@ class OutputFile {
   bool write(const std::string &s) { return s.empty() || fwrite(s.data(), 1, s.size(), f_) == s.size(); }
   bool close() {
     bool ok = true;
-    if (f_) ok = fclose(f_) == 0, f_ = nullptr;
+    if (f_ && format_ == 'g') ok = fwrite(BGZF_EOF, 1, sizeof BGZF_EOF, f_) == sizeof BGZF_EOF; /* bgzip's end marker */
+    if (f_) ok = (fclose(f_) == 0) && ok, f_ = nullptr;
     if (pid_ > 0) {
       int st = 0;
       waitpid(pid_, &st, 0);
@@ -772,7 +961,9 @@ static int run_pipeline(const Decider &dec, const nh_files_t *files, nh_run_stat
 
   std::string err;
   RecordReader readers[2];
-  if (!readers[0].open(files->in1, err) || (paired && !readers[1].open(files->in2, err)))
+  /* inflate threads per input file (only blocked gzip can use more than one) */
+  const int in_threads = std::max(1, std::min(8, threads / nf));
+  if (!readers[0].open(files->in1, in_threads, err) || (paired && !readers[1].open(files->in2, in_threads, err)))
     return nh_set_error(NH_ERR_IO, "%s", err.c_str());
   OutputFile outs[2];
   /* like src/main.rs:342-346: one output gets all the threads, two share them */

@@ -213,3 +213,48 @@ def test_unusual_but_valid_endings(tmp_path):
     st = rewrite_files(keep, call, d, tmp_path / "o4.fa")
     assert st.total == 3
     assert open(tmp_path / "o4.fa", "rb").read() == b">s1 desc\nacgtnACGT\n>s2\n\n>s3\nTT\n"
+
+
+def test_gzip_output_is_bgzf_and_is_read_back_in_parallel(tmp_path):
+    """gzip output = BGZF (members <= 64 KiB with a 'BC' size subfield + bgzip's EOF marker); such input
+    (bgzip, bcl2fastq, our own output) is inflated by several threads and must give identical records"""
+    import struct
+    import zlib
+    n = 30000
+    r1, r2 = make_records(n, seed=11), make_records(n, seed=12)
+    keep, call = np.ones(n, np.uint8), np.zeros(n, np.uint32)
+    i1, i2 = tmp_path / "p_1.fq", tmp_path / "p_2.fq"
+    write_input(i1, r1)
+    write_input(i2, r2)
+    g1, g2 = tmp_path / "g_1.fq.gz", tmp_path / "g_2.fq.gz"
+    rewrite_files(keep, call, i1, g1, i2, g2, out_format="g", threads=4)
+    raw = open(g1, "rb").read()
+    assert raw[:4] == b"\x1f\x8b\x08\x04" and raw[12:16] == b"BC\x02\x00"
+    assert raw.endswith(bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000"))
+    # walk the members by their announced sizes
+    pos, members, total = 0, 0, 0
+    while pos < len(raw):
+        bsize = struct.unpack_from("<H", raw, pos + 16)[0] + 1
+        isize = struct.unpack_from("<I", raw, pos + bsize - 4)[0]
+        assert isize <= 0xFF00 and bsize <= 65536
+        assert len(zlib.decompress(raw[pos + 18:pos + bsize - 8], wbits=-15)) == isize
+        total += isize
+        members += 1
+        pos += bsize
+    assert pos == len(raw) and members > 50 and total == len(expected(r1, keep, call))
+    assert gzip.decompress(raw) == expected(r1, keep, call)
+    assert subprocess.run(["gzip", "-t", str(g1)]).returncode == 0
+    # read it back with 8 threads (parallel member inflate) and with 1 (zlib's gzread): same bytes
+    for threads in (8, 1):
+        o1, o2 = tmp_path / f"back{threads}_1.fq", tmp_path / f"back{threads}_2.fq"
+        st = rewrite_files(keep, call, g1, o1, g2, o2, out_format="u", threads=threads)
+        assert st.total == n
+        assert open(o1, "rb").read() == expected(r1, keep, call)
+        assert open(o2, "rb").read() == expected(r2, keep, call)
+    # a damaged member is an error, not silence
+    bad = bytearray(raw)
+    bad[len(bad) // 2] ^= 0x55
+    b1 = tmp_path / "bad_1.fq.gz"
+    b1.write_bytes(bytes(bad))
+    with pytest.raises(NhError):
+        rewrite_files(keep, call, b1, tmp_path / "x1.fq", g2, tmp_path / "x2.fq", threads=8)

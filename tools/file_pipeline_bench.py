@@ -63,12 +63,18 @@ def main():
     fastq_array(seqs[1::2], 2).tofile(p2)
     subprocess.check_call(["gzip", "-k", "-1", p1])
     subprocess.check_call(["gzip", "-k", "-1", p2])
+    # blocked gzip (BGZF, what bgzip / bcl2fastq / this library write) of the same reads, made with the host-only hook
+    from nohuman_b200.api import rewrite_files
+    b1, b2 = os.path.join(d, "b_1.fq.gz"), os.path.join(d, "b_2.fq.gz")
+    rewrite_files(np.ones(args.pairs, np.uint8), np.zeros(args.pairs, np.uint32), p1, b1, p2, b2, out_format="g",
+                  threads=args.threads)
     cli = os.path.join(ROOT, "nohuman_b200", "bin", "nohuman")
     rows = []
     gbp = args.pairs * 2 * L / 1e9
     for name, a, b, fmt in (("plain in, plain out", p1, p2, "u"), ("plain in, gzip out", p1, p2, "g"),
                             ("gzip in, gzip out (configs[1])", p1 + ".gz", p2 + ".gz", "g"),
-                            ("gzip in, plain out", p1 + ".gz", p2 + ".gz", "u")):
+                            ("gzip in, plain out", p1 + ".gz", p2 + ".gz", "u"),
+                            ("blocked gzip in, plain out", b1, b2, "u"), ("blocked gzip in, gzip out", b1, b2, "g")):
         o1, o2 = os.path.join(d, "o1"), os.path.join(d, "o2")
         t0 = time.perf_counter()
         r = subprocess.run([cli, "-v", "--db", db_dir, "-t", str(args.threads), "--conf", "0.5", "-F", fmt, "-o", o1, "-O", o2, a, b],
