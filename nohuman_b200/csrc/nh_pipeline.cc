@@ -187,39 +187,53 @@ class BgzfReader {
   }
 
  private:
+  /* one task = up to NH_BGZF_BATCH consecutive members (fewer wake-ups than one per 64 KiB member) */
+  static constexpr int NH_BGZF_BATCH = 16;
   struct Blk {
     std::string comp, raw;
+    std::vector<uint32_t> clen; /* deflate bytes + 8-byte trailer of each member in comp */
     bool done = false, ok = true;
   };
   void produce() {
-    for (;;) {
-      unsigned char hdr[12 + 65536];
-      size_t n = fread(hdr, 1, 12, f_);
-      bool bad = false;
+    bool at_end = false;
+    while (!at_end) {
       auto b = std::make_shared<Blk>();
-      if (n == 0) {
-        /* clean end of file */
-      } else {
+      bool bad = false;
+      for (int k = 0; k < NH_BGZF_BATCH; k++) {
+        unsigned char hdr[12 + 65536];
+        size_t n = fread(hdr, 1, 12, f_);
+        if (n == 0) { /* clean end of file */
+          at_end = true;
+          break;
+        }
         size_t xlen = n == 12 ? (hdr[10] | (size_t)hdr[11] << 8) : 0, bsize = 0;
         if (n != 12 || fread(hdr + 12, 1, xlen, f_) != xlen || !bgzf_block_size(hdr, 12 + xlen, &xlen, &bsize) ||
             bsize < 12 + xlen + 8) {
           bad = true;
-        } else {
-          b->comp.resize(bsize - 12 - xlen);
-          if (fread(&b->comp[0], 1, b->comp.size(), f_) != b->comp.size()) bad = true;
+          break;
         }
+        const size_t len = bsize - 12 - xlen, at = b->comp.size();
+        b->comp.resize(at + len);
+        if (fread(&b->comp[at], 1, len, f_) != len) {
+          bad = true;
+          break;
+        }
+        b->clen.push_back((uint32_t)len);
       }
       std::unique_lock<std::mutex> lk(m_);
-      if (n == 0 || bad) {
-        if (bad) error_ = true;
+      if (bad) {
+        error_ = true;
         eof_ = true;
         cv_.notify_all();
         return;
       }
-      space_.wait(lk, [&] { return order_.size() < 512 || stop_; });
-      if (stop_) return;
-      order_.push_back(b);
-      todo_.push_back(b);
+      if (!b->clen.empty()) {
+        space_.wait(lk, [&] { return order_.size() < 64 || stop_; });
+        if (stop_) return;
+        order_.push_back(b);
+        todo_.push_back(b);
+      }
+      if (at_end) eof_ = true;
       cv_.notify_all();
     }
   }
@@ -237,19 +251,32 @@ class BgzfReader {
         b = todo_.front();
         todo_.pop_front();
       }
-      const size_t clen = b->comp.size() - 8;
-      const unsigned char *tr = (const unsigned char *)b->comp.data() + clen;
-      const uint32_t crc = tr[0] | tr[1] << 8 | tr[2] << 16 | (uint32_t)tr[3] << 24;
-      const uint32_t isize = tr[4] | tr[5] << 8 | tr[6] << 16 | (uint32_t)tr[7] << 24;
-      b->raw.resize(isize);
-      inflateReset(&zs);
-      zs.next_in = (Bytef *)b->comp.data();
-      zs.avail_in = (uInt)clen;
-      zs.next_out = (Bytef *)(isize ? &b->raw[0] : nullptr);
-      zs.avail_out = isize;
-      const int rc = isize ? inflate(&zs, Z_FINISH) : Z_STREAM_END;
-      const bool ok = rc == Z_STREAM_END && zs.total_out == isize &&
-                      (uint32_t)crc32(crc32(0L, Z_NULL, 0), (const Bytef *)b->raw.data(), isize) == crc;
+      bool ok = true;
+      size_t total = 0, at = 0;
+      for (uint32_t len : b->clen) {
+        const unsigned char *tr = (const unsigned char *)b->comp.data() + at + len - 8;
+        total += tr[4] | tr[5] << 8 | tr[6] << 16 | (size_t)tr[7] << 24;
+        at += len;
+      }
+      b->raw.resize(total);
+      size_t out_at = 0;
+      at = 0;
+      for (uint32_t len : b->clen) {
+        const size_t clen = len - 8;
+        const unsigned char *tr = (const unsigned char *)b->comp.data() + at + clen;
+        const uint32_t crc = tr[0] | tr[1] << 8 | tr[2] << 16 | (uint32_t)tr[3] << 24;
+        const uint32_t isize = tr[4] | tr[5] << 8 | tr[6] << 16 | (uint32_t)tr[7] << 24;
+        inflateReset(&zs);
+        zs.next_in = (Bytef *)b->comp.data() + at;
+        zs.avail_in = (uInt)clen;
+        zs.next_out = (Bytef *)(isize ? &b->raw[out_at] : nullptr);
+        zs.avail_out = isize;
+        const int rc = isize ? inflate(&zs, Z_FINISH) : Z_STREAM_END;
+        ok = ok && rc == Z_STREAM_END && zs.total_out == isize &&
+             (uint32_t)crc32(crc32(0L, Z_NULL, 0), (const Bytef *)b->raw.data() + out_at, isize) == crc;
+        out_at += isize;
+        at += len;
+      }
       std::string().swap(b->comp);
       std::lock_guard<std::mutex> lk(m_);
       b->ok = ok;
