@@ -178,7 +178,8 @@ typedef struct {
   const char *in2;            /* second mate file, or NULL for single-end */
   const char *out1;           /* where kept records of in1 go */
   const char *out2;           /* ... of in2 (paired only) */
-  int32_t out_format;         /* nohuman -F letter: 'u' none, 'g' gzip, 'b' bzip2, 'x' xz, 'z' zstd; 0 = 'u' */
+  int32_t out_format;         /* nohuman -F letter: 'u' none, 'g' gzip (written as BGZF members), 'b' bzip2,
+                                 'x' xz, 'z' zstd; 0 = 'u' */
   int32_t tag_classified;     /* 1: append " kraken:taxid|<id>" to classified-out headers as kraken2 does */
   const char *kraken_output;  /* --output: per-read lines; NULL or "/dev/null": not produced */
   const char *kraken_report;  /* --report; NULL: not produced */
