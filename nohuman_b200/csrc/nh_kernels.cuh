@@ -10,7 +10,9 @@
 
 #include "nh_math.h"
 
+#ifndef NH_WARPS_PER_BLOCK
 #define NH_WARPS_PER_BLOCK 8
+#endif
 #define NH_BLOCK_THREADS (NH_WARPS_PER_BLOCK * 32)
 #define NH_TILE_LMERS 128           /* l-mers per minimizer tile of the warp-per-tile kernel (4 warp iterations) */
 #define NH_FUSED_TILE_POS 252       /* k-mer positions per tile of the lane-serial fused kernel (<= 255) */

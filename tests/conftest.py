@@ -14,6 +14,13 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run with -m gpu on the B200 box)")
 
 
+@pytest.fixture(scope="session", autouse=True)
+def ensure_built():
+    """The library and the CLI are built in-tree (python -m nohuman_b200.build); rebuild only if stale or missing."""
+    from nohuman_b200 import build
+    build.build()
+
+
 @pytest.fixture(scope="session")
 def oracle():
     from oracle import k2oracle
