@@ -372,7 +372,7 @@ k_minimizers(const NhDbParams db, const NhBatchPtrs b) {
 __device__ __forceinline__ void ld_sector(const uint32_t *p, uint32_t (&c)[8]) {
   /* one 32-byte sector in one request (256-bit global load, sm_100+) */
 #ifndef NH_LD_SECTOR_OP
-#define NH_LD_SECTOR_OP "ld.global.nc.L1::no_allocate.v8.u32"
+#define NH_LD_SECTOR_OP "ld.global.nc.L1::no_allocate.L2::64B.v8.u32"
 #endif
   asm volatile(NH_LD_SECTOR_OP " {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                : "=r"(c[0]), "=r"(c[1]), "=r"(c[2]), "=r"(c[3]), "=r"(c[4]), "=r"(c[5]),
@@ -1121,14 +1121,20 @@ k_scan_probe_score(const NhDbParams db, const NhBatchPtrs b, const NhScoreParams
  * their lookups written to global memory for k_score / k_gather_runs.
  */
 
+#ifndef NH_STREAM_TMA
+#define NH_STREAM_TMA 1
+#endif
+#define NH_BCHUNK_WORDS 8u                          /* base words (4 bases each) per lane and chunk */
+#define NH_BCHUNK_STRIDE (NH_BCHUNK_WORDS * 4u + 16u) /* + up to 12 bytes of 16-byte misalignment */
+
 struct __align__(16) StreamWarpSmem {
   uint64_t pq_key[128];                  /* closed runs waiting to be probed (ring) */
   uint32_t pq_slot[128];
   uint16_t pq_meta[128];                 /* owner lane | k-mer count << 5 | first lookup of its tile << 13 */
-  uint32_t q_unit[64];                   /* probe chains that continue into the next sector */
-  uint32_t q_ckey[64];
-  uint32_t q_slot[64];
-  uint32_t q_aux[64];                    /* owner lane | k-mer count << 5 | first << 13 | sectors visited << 14 */
+  uint32_t q_unit[32];                   /* probe chains that continue into the next sector (at most one per lane) */
+  uint32_t q_ckey[32];
+  uint32_t q_slot[32];
+  uint32_t q_aux[32];                    /* owner lane | k-mer count << 5 | first << 13 | sectors visited << 14 */
   uint64_t first_min[32], last_min[32];  /* first / last distinct minimizer of each lane's tile */
   uint32_t keys[NH_LANE_TAXA * 32];      /* taxon tables, [slot][owner lane] */
   uint32_t cnts[NH_LANE_TAXA * 32];
@@ -1136,9 +1142,57 @@ struct __align__(16) StreamWarpSmem {
   uint8_t meta[32];                      /* per tile: owner lane (the lane before, for a second mate) */
   uint32_t overflow;                     /* bit per owner lane: table overflowed */
   uint32_t first_hit;                    /* bit per lane: the tile's first lookup hit */
+#if NH_STREAM_TMA
+  /* base staging: every lane's next NH_BCHUNK_WORDS words arrive by asynchronous 16-byte copies
+   * (cp.async, completion on an mbarrier) into its own 48-byte window, double-buffered.  The scan then reads
+   * bases with LDS only: a global base-word load shares its scoreboard with the table sector
+   * loads (ptxas puts every LDG on SB5), so a lane waiting for 4 bases also waited ~1 us for the
+   * sector read the probe round had just issued. */
+  uint64_t bbar[2];
+  __align__(16) uint8_t bchunk[2][32 * NH_BCHUNK_STRIDE];
+  /* table sectors land here too (one 32-byte sector per lane and probe round): a register
+   * destination would keep a load scoreboard busy, and ptxas drains every scoreboard at the first
+   * potentially divergent branch, i.e. a few instructions after the round instead of one round later */
+  uint64_t sbar;
+  __align__(16) uint32_t sect[32 * 8];
+#endif
 };
 
 #define NH_AUX_NONE 0xFFFFFFFFu
+
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+/* 16 bytes global -> shared without a register or a load scoreboard in between (LDGSTS, L2 only) */
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async16_l2_64(uint32_t dst, const void *src) {
+  asm volatile("cp.async.cg.shared.global.L2::64B [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+/* the mbarrier gets this thread's arrival once all its earlier cp.async copies have landed */
+__device__ __forceinline__ void cp_async_arrive(uint32_t bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "NH_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra NH_DONE;\n"
+      "bra NH_WAIT;\n"
+      "NH_DONE:\n"
+      "}" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
 
 /* 3 blocks of 8 warps per SM (up to 85 registers): with the overlap happening inside the warp,
  * registers are worth more than resident warps (measured 3.14 ms at 80 registers / 24 warps
@@ -1177,6 +1231,22 @@ k_stream_classify(const NhDbParams db, const NhBatchPtrs b, const NhScoreParams 
   /* probe-chain guard for a table without any empty cell (never a real database) */
   const uint32_t max_visits = n_sectors + 1u < 0x3FFFFu ? n_sectors + 1u : 0x3FFFFu;
   uint32_t tot_lookups = 0, tot_classified = 0, tot_kept = 0;
+#if NH_STREAM_TMA
+  const uint32_t bar0 = smem_addr(&sm.bbar[0]);
+  const uint32_t win0 = smem_addr(&sm.bchunk[0][lane * NH_BCHUNK_STRIDE]);
+  uint32_t bar_par = 0; /* bit per buffer: parity of the phase its next chunk completes (warp-uniform) */
+  const uint32_t sbar = smem_addr(&sm.sbar);
+  const uint32_t sect0 = smem_addr(&sm.sect[0]);
+  uint32_t sect_par = 0; /* parity of the phase the sectors in flight complete */
+  if (lane == 0) {
+    mbar_init(bar0, 32u); /* every lane arrives once per chunk, when its copies have landed */
+    mbar_init(bar0 + 8u, 32u);
+    mbar_init(sbar, 32u);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncwarp();
+#endif
 
   /* groups of 32 tiles are handed out through a counter: warps that draw short tiles take more */
   for (;;) {
@@ -1220,6 +1290,16 @@ k_stream_classify(const NhDbParams db, const NhBatchPtrs b, const NhScoreParams 
         const bool active = f_aux != NH_AUX_NONE;
         bool done = false;
         uint32_t result = 0;
+#if NH_STREAM_TMA
+        mbar_wait(sbar, sect_par);
+        sect_par ^= 1u;
+        {
+          const uint4 lo = *reinterpret_cast<const uint4 *>(&sm.sect[lane * 8u]);
+          const uint4 hi = *reinterpret_cast<const uint4 *>(&sm.sect[lane * 8u + 4u]);
+          c[0] = lo.x; c[1] = lo.y; c[2] = lo.z; c[3] = lo.w;
+          c[4] = hi.x; c[5] = hi.y; c[6] = hi.z; c[7] = hi.w;
+        }
+#endif
         if (active) {
           uint32_t range = 0xFFu << f_start;
           if (f_unit == last_sector) range &= last_range;
@@ -1305,8 +1385,24 @@ k_stream_classify(const NhDbParams db, const NhBatchPtrs b, const NhScoreParams 
       cq_n -= n_cq;
       pq_head = (pq_head + n_pq) & 127u;
       pq_n -= n_pq;
-      if (f_aux != NH_AUX_NONE) ld_sector(db.cells + (uint64_t)f_unit * 8ULL, c);
       any_inflight = (n_cq + n_pq) != 0u;
+#if NH_STREAM_TMA
+      if (any_inflight) {
+        /* lane pairs fetch the two 16-byte halves of one sector with ONE instruction, so a sector
+         * stays one request (request = warp instruction x 128-byte line):
+         * the first instruction covers the sectors of lanes 0-15, the second those of lanes 16-31 */
+        const uint32_t mine = f_aux != NH_AUX_NONE ? f_unit : 0xFFFFFFFFu;
+        const uint32_t half = lane & 1u, src_lane = lane >> 1;
+        const uint32_t u0 = __shfl_sync(FULL_MASK, mine, src_lane);
+        const uint32_t u1 = __shfl_sync(FULL_MASK, mine, 16u + src_lane);
+        const uint32_t dst = sect0 + src_lane * 32u + half * 16u;
+        if (u0 != 0xFFFFFFFFu) cp_async16_l2_64(dst, db.cells + (uint64_t)u0 * 8ULL + half * 4u);
+        if (u1 != 0xFFFFFFFFu) cp_async16_l2_64(dst + 512u, db.cells + (uint64_t)u1 * 8ULL + half * 4u);
+        cp_async_arrive(sbar);
+      }
+#else
+      if (f_aux != NH_AUX_NONE) ld_sector(db.cells + (uint64_t)f_unit * 8ULL, c);
+#endif
       __syncwarp(); /* queue slots just read may be overwritten by the next pushes */
     };
 
@@ -1375,23 +1471,13 @@ k_stream_classify(const NhDbParams db, const NhBatchPtrs b, const NhScoreParams 
         }
       };
 
-      uint32_t codes = 0, ambs = 0;
-      /* words are loaded NH_STREAM_PREFETCH iterations ahead of their use: a lane's 4-byte load is
-       * its own request into a memory system kept busy by the random table reads */
-      uint32_t w_q[NH_STREAM_PREFETCH];
-#pragma unroll
-      for (int pf = 0; pf < NH_STREAM_PREFETCH; pf++) w_q[pf] = (uint32_t)pf < my_words ? __ldg(q + pf) : 0u;
-      for (uint32_t base_i = 0; base_i < max_words * 4u; base_i += 4u) {
+      /* four bases (one 4-byte word of the word-aligned stream, first base at stream index base_i) */
+      auto scan_word = [&](const uint32_t word, const uint32_t base_i) {
+        uint32_t ambs;
+        const uint32_t codes = nh_pack4(word, &ambs); /* first base in bits 7..6 */
 #pragma unroll
         for (int j = 0; j < 4; j++) {
           const uint32_t i = base_i + (uint32_t)j; /* index in the word-aligned stream */
-          if (j == 0) {
-            codes = nh_pack4(w_q[0], &ambs); /* first base in bits 7..6 */
-#pragma unroll
-            for (int pf = 0; pf + 1 < NH_STREAM_PREFETCH; pf++) w_q[pf] = w_q[pf + 1];
-            const uint32_t wi = (base_i >> 2) + NH_STREAM_PREFETCH;
-            w_q[NH_STREAM_PREFETCH - 1] = wi < my_words ? __ldg(q + wi) : 0u;
-          }
           const uint32_t cc = (codes >> (6u - 2u * (uint32_t)j)) & 3u;
           const bool inside = i >= mis && i < end_idx;
           /* bytes outside the tile count as ambiguous: they reset the l-mer and never reach a position */
@@ -1437,7 +1523,56 @@ k_stream_classify(const NhDbParams db, const NhBatchPtrs b, const NhScoreParams 
 #endif
           }
         }
+      };
+
+#if NH_STREAM_TMA
+      /* the lane's window for chunk c: bytes [32c, 32c + 48) from src0, the 16-byte block holding word 0 */
+      const uint32_t a16 = (uint32_t)((uintptr_t)q & 15u);
+      const uint8_t *src0 = reinterpret_cast<const uint8_t *>(q) - a16;
+      const uint32_t my_bytes = my_words ? a16 + my_words * 4u : 0u;
+      const uint32_t n_chunks = (max_words + NH_BCHUNK_WORDS - 1u) / NH_BCHUNK_WORDS;
+      auto stage = [&](const uint32_t ch) {
+        const uint32_t buf = ch & 1u;
+        const uint32_t lo = ch * (NH_BCHUNK_WORDS * 4u);
+        const uint32_t dst = win0 + buf * (32u * NH_BCHUNK_STRIDE);
+#pragma unroll
+        for (uint32_t pc = 0; pc < NH_BCHUNK_STRIDE; pc += 16u)
+          if (lo + pc < my_bytes) cp_async16(dst + pc, src0 + lo + pc);
+        cp_async_arrive(bar0 + buf * 8u);
+      };
+      if (n_chunks) stage(0u);
+      for (uint32_t ch = 0; ch < n_chunks; ch++) {
+        if (ch + 1u < n_chunks) stage(ch + 1u); /* its buffer was read two chunks ago (syncwarp below) */
+        const uint32_t buf = ch & 1u;
+        mbar_wait(bar0 + buf * 8u, (bar_par >> buf) & 1u);
+        bar_par ^= 1u << buf;
+        const uint32_t wbase = win0 + buf * (32u * NH_BCHUNK_STRIDE) + a16;
+        const uint32_t w0 = ch * NH_BCHUNK_WORDS;
+        const uint32_t wn = max_words - w0 < NH_BCHUNK_WORDS ? max_words - w0 : NH_BCHUNK_WORDS;
+        uint32_t w_next = lds_u32(wbase);
+#pragma unroll 1
+        for (uint32_t w = 0; w < wn; w++) {
+          const uint32_t word = w_next;
+          w_next = lds_u32(wbase + (((w + 1u) & (NH_BCHUNK_WORDS - 1u)) << 2)); /* one word ahead; the wrap is a harmless re-read */
+          scan_word(word, (w0 + w) * 4u);
+        }
+        __syncwarp(); /* every lane is done with this buffer before chunk ch + 2 lands in it */
       }
+#else
+      /* words are loaded NH_STREAM_PREFETCH iterations ahead of their use: a lane's 4-byte load is
+       * its own request into a memory system kept busy by the random table reads */
+      uint32_t w_q[NH_STREAM_PREFETCH];
+#pragma unroll
+      for (int pf = 0; pf < NH_STREAM_PREFETCH; pf++) w_q[pf] = (uint32_t)pf < my_words ? __ldg(q + pf) : 0u;
+      for (uint32_t base_i = 0; base_i < max_words * 4u; base_i += 4u) {
+        const uint32_t word = w_q[0];
+#pragma unroll
+        for (int pf = 0; pf + 1 < NH_STREAM_PREFETCH; pf++) w_q[pf] = w_q[pf + 1];
+        const uint32_t wi = (base_i >> 2) + NH_STREAM_PREFETCH;
+        w_q[NH_STREAM_PREFETCH - 1] = wi < my_words ? __ldg(q + wi) : 0u;
+        scan_word(word, base_i);
+      }
+#endif
       emit(cnt != 0u, last, cnt);
       if (scanning) {
         NhTileOut o;
@@ -1626,7 +1761,7 @@ int nh_launch_plan(const NhDbParams &db, const NhBatchPtrs &b, cudaStream_t st) 
 
 bool nh_fused_supported(const NhDbParams &db) {
   /* window of 5 l-mers, u8 run lengths, u32 group indices (tables below 128 GiB) */
-  return db.w == 5 && db.tile_pos <= 255 && db.capacity < (1ULL << 35);
+  return db.w == 5 && db.tile_pos <= 255 && db.capacity < (1ULL << 35) - 8ULL; /* sector index 0xFFFFFFFF is "none" */
 }
 
 static size_t fused_smem_bytes(const NhDbParams &db) {

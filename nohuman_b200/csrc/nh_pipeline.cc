@@ -34,6 +34,8 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <errno.h>
+#include <sys/socket.h>
 #include <sys/stat.h>
 #include <sys/wait.h>
 #include <unistd.h>
@@ -59,6 +61,9 @@ extern char **environ;
 namespace {
 
 constexpr size_t NH_CHUNK_RECORDS = 1u << 16; /* records per reader chunk (per file) */
+constexpr uint64_t NH_CHUNK_BASES = 48u << 20;  /* ... or this many bases in the first file's chunk, whichever comes first */
+constexpr size_t NH_CHUNK_TEXT = 1u << 30;      /* ... or this much header + sequence + quality text */
+constexpr uint64_t NH_BATCH_BASES = 64u << 20;  /* bases per nh_classify_batch call (session capacity; grows for a longer single unit) */
 constexpr size_t NH_OUT_BLOCK = 1u << 20;     /* uncompressed bytes per compression block */
 
 /* ------------------------------------------------------------------ */
@@ -135,6 +140,69 @@ static bool bgzf_block_size(const unsigned char *hdr, size_t n, size_t *xlen, si
   return false;
 }
 
+/* Streaming inflate of ordinary gzip (any number of concatenated members), restating what zlib's
+ * gzread does for kraken2's reader — except that a stream that ends inside a member is an ERROR
+ * here, where gzread hands back the bytes it has and only flags Z_BUF_ERROR in gzerror(). */
+class GzipStream {
+ public:
+  ~GzipStream() {
+    if (init_) inflateEnd(&zs_);
+  }
+  /* `f` is positioned at the first byte of a gzip member; `pre` = bytes already consumed from it */
+  bool begin(FILE *f, const unsigned char *pre, size_t n_pre) {
+    f_ = f;
+    in_.resize(1u << 20);
+    memcpy(&in_[0], pre, n_pre);
+    zs_ = z_stream{};
+    if (inflateInit2(&zs_, 15 + 16) != Z_OK) return false;
+    init_ = true;
+    zs_.next_in = (Bytef *)&in_[0];
+    zs_.avail_in = (uInt)n_pre;
+    return true;
+  }
+  /* fills `out` (capacity bytes); returns bytes produced, 0 at the clean end, -1 on a corrupt or truncated stream */
+  long read(char *out, size_t cap) {
+    if (done_) return 0;
+    zs_.next_out = (Bytef *)out;
+    zs_.avail_out = (uInt)cap;
+    while (zs_.avail_out > 0) {
+      if (zs_.avail_in == 0) {
+        const size_t n = fread(&in_[0], 1, in_.size(), f_);
+        if (n == 0) {
+          if (ferror(f_) || in_member_) return -1; /* the file ends inside a member: truncated */
+          done_ = true;
+          break;
+        }
+        zs_.next_in = (Bytef *)&in_[0];
+        zs_.avail_in = (uInt)n;
+      }
+      if (!in_member_) {
+        /* between members: another gzip header continues the stream, anything else is trailing
+         * garbage, which gzread ignores */
+        if (zs_.next_in[0] != 0x1f) {
+          done_ = true;
+          break;
+        }
+        inflateReset(&zs_);
+        in_member_ = true;
+      }
+      const int rc = inflate(&zs_, Z_NO_FLUSH);
+      if (rc == Z_STREAM_END) {
+        in_member_ = false;
+      } else if (rc != Z_OK && rc != Z_BUF_ERROR) {
+        return -1;
+      }
+    }
+    return (long)(cap - zs_.avail_out);
+  }
+
+ private:
+  FILE *f_ = nullptr;
+  z_stream zs_{};
+  std::string in_;
+  bool init_ = false, in_member_ = true, done_ = false;
+};
+
 class BgzfReader {
  public:
   ~BgzfReader() { close(); }
@@ -146,31 +214,21 @@ class BgzfReader {
     for (int i = 0; i < threads; i++) workers_.emplace_back([this] { work(); });
     return true;
   }
-  long read(char *buf, size_t n) {
-    size_t got = 0;
-    while (got < n) {
-      std::shared_ptr<Blk> b;
-      {
-        std::unique_lock<std::mutex> lk(m_);
-        cv_.wait(lk, [&] { return (!order_.empty() && order_.front()->done) || (eof_ && order_.empty()) || error_; });
-        if (error_) return -1;
-        if (order_.empty()) break;
-        b = order_.front();
-        if (!b->ok) return -1;
-      }
-      const size_t avail = b->raw.size() - off_;
-      const size_t take = avail < n - got ? avail : n - got;
-      memcpy(buf + got, b->raw.data() + off_, take);
-      got += take;
-      off_ += take;
-      if (off_ == b->raw.size()) {
-        std::lock_guard<std::mutex> lk(m_);
-        order_.pop_front();
-        off_ = 0;
-        space_.notify_all();
-      }
+  /* next run of inflated bytes, in file order; 0 at the end, -1 on error */
+  long next(std::string &out) {
+    std::shared_ptr<Blk> b;
+    {
+      std::unique_lock<std::mutex> lk(m_);
+      cv_.wait(lk, [&] { return (!order_.empty() && order_.front()->done) || (eof_ && order_.empty()) || error_; });
+      if (error_) return -1;
+      if (order_.empty()) return 0;
+      b = order_.front();
+      if (!b->ok) return -1;
+      order_.pop_front();
+      space_.notify_all();
     }
-    return (long)got;
+    out.swap(b->raw);
+    return (long)out.size();
   }
   void close() {
     {
@@ -194,21 +252,72 @@ class BgzfReader {
     std::vector<uint32_t> clen; /* deflate bytes + 8-byte trailer of each member in comp */
     bool done = false, ok = true;
   };
+  bool enqueue(std::shared_ptr<Blk> b, bool inflated) {
+    std::unique_lock<std::mutex> lk(m_);
+    space_.wait(lk, [&] { return order_.size() < 64 || stop_; });
+    if (stop_) return false;
+    b->done = inflated;
+    order_.push_back(b);
+    if (!inflated) todo_.push_back(b);
+    cv_.notify_all();
+    return true;
+  }
+  void fail() {
+    std::lock_guard<std::mutex> lk(m_);
+    error_ = true;
+    eof_ = true;
+    cv_.notify_all();
+  }
+  /* A member without the BC subfield (e.g. `cat blocked.gz plain.gz`): zlib and kraken2 read such a
+   * file, so the rest of it is inflated as an ordinary gzip stream on this thread. */
+  void serial_tail(const unsigned char *pre, size_t n_pre) {
+    GzipStream gs;
+    if (!gs.begin(f_, pre, n_pre)) return fail();
+    for (;;) {
+      auto b = std::make_shared<Blk>();
+      b->raw.resize(1u << 20);
+      const long n = gs.read(&b->raw[0], b->raw.size());
+      if (n < 0) return fail();
+      if (n == 0) break;
+      b->raw.resize((size_t)n);
+      if (!enqueue(b, true)) return;
+    }
+    std::lock_guard<std::mutex> lk(m_);
+    eof_ = true;
+    cv_.notify_all();
+  }
   void produce() {
     bool at_end = false;
     while (!at_end) {
       auto b = std::make_shared<Blk>();
-      bool bad = false;
+      bool bad = false, plain_member = false;
+      unsigned char hdr[12 + 65536];
+      size_t n_hdr = 0;
       for (int k = 0; k < NH_BGZF_BATCH; k++) {
-        unsigned char hdr[12 + 65536];
         size_t n = fread(hdr, 1, 12, f_);
+        n_hdr = n;
         if (n == 0) { /* clean end of file */
           at_end = true;
           break;
         }
+        if (n == 12 && hdr[0] == 0x1f && hdr[1] == 0x8b && !(hdr[3] & 4)) { /* gzip, but no extra field */
+          plain_member = true;
+          break;
+        }
         size_t xlen = n == 12 ? (hdr[10] | (size_t)hdr[11] << 8) : 0, bsize = 0;
-        if (n != 12 || fread(hdr + 12, 1, xlen, f_) != xlen || !bgzf_block_size(hdr, 12 + xlen, &xlen, &bsize) ||
-            bsize < 12 + xlen + 8) {
+        if (n != 12 || fread(hdr + 12, 1, xlen, f_) != xlen) {
+          bad = true;
+          break;
+        }
+        n_hdr = 12 + xlen;
+        if (!bgzf_block_size(hdr, 12 + xlen, &xlen, &bsize)) {
+          if (hdr[0] == 0x1f && hdr[1] == 0x8b)
+            plain_member = true; /* extra field without BC */
+          else
+            bad = true; /* not gzip at all: gzread would stop here; a blocked file never has trailing garbage */
+          break;
+        }
+        if (bsize < 12 + xlen + 8) {
           bad = true;
           break;
         }
@@ -220,21 +329,14 @@ class BgzfReader {
         }
         b->clen.push_back((uint32_t)len);
       }
-      std::unique_lock<std::mutex> lk(m_);
-      if (bad) {
-        error_ = true;
+      if (bad) return fail();
+      if (!b->clen.empty() && !enqueue(b, false)) return;
+      if (plain_member) return serial_tail(hdr, n_hdr);
+      if (at_end) {
+        std::lock_guard<std::mutex> lk(m_);
         eof_ = true;
         cv_.notify_all();
-        return;
       }
-      if (!b->clen.empty()) {
-        space_.wait(lk, [&] { return order_.size() < 64 || stop_; });
-        if (stop_) return;
-        order_.push_back(b);
-        todo_.push_back(b);
-      }
-      if (at_end) eof_ = true;
-      cv_.notify_all();
     }
   }
   void work() {
@@ -255,13 +357,16 @@ class BgzfReader {
       size_t total = 0, at = 0;
       for (uint32_t len : b->clen) {
         const unsigned char *tr = (const unsigned char *)b->comp.data() + at + len - 8;
-        total += tr[4] | tr[5] << 8 | tr[6] << 16 | (size_t)tr[7] << 24;
+        const size_t isize = tr[4] | tr[5] << 8 | tr[6] << 16 | (size_t)tr[7] << 24;
+        if (isize > 65536) ok = false; /* the BGZF limit; also bounds the allocation below */
+        total += isize;
         at += len;
       }
-      b->raw.resize(total);
+      if (ok) b->raw.resize(total);
       size_t out_at = 0;
       at = 0;
       for (uint32_t len : b->clen) {
+        if (!ok) break;
         const size_t clen = len - 8;
         const unsigned char *tr = (const unsigned char *)b->comp.data() + at + clen;
         const uint32_t crc = tr[0] | tr[1] << 8 | tr[2] << 16 | (uint32_t)tr[3] << 24;
@@ -291,10 +396,12 @@ class BgzfReader {
   std::mutex m_;
   std::condition_variable cv_, space_;
   std::deque<std::shared_ptr<Blk>> order_, todo_;
-  size_t off_ = 0;
   bool eof_ = false, error_ = false, stop_ = false;
 };
 
+/* Decompressed bytes of one input file, produced ahead of the parser by a thread of its own
+ * (blocked gzip: by the BgzfReader's pool), so that inflate and FASTQ parsing overlap.  The reference
+ * leaves this to kraken2, which inflates inline in its reader (src/main.rs:267 hands it the paths). */
 class InputStream {
  public:
   ~InputStream() { close(); }
@@ -306,10 +413,10 @@ class InputStream {
     }
     unsigned char magic[64] = {0};
     size_t n = fread(magic, 1, sizeof magic, f);
-    fclose(f);
     size_t xlen = 0, bsize = 0;
     if (threads > 1 && bgzf_block_size(magic, n, &xlen, &bsize)) {
       /* blocked gzip: members inflated in parallel */
+      fclose(f);
       bgzf_.reset(new BgzfReader());
       if (!bgzf_->open(path, threads)) {
         err = "cannot open " + path;
@@ -317,7 +424,18 @@ class InputStream {
       }
       return true;
     }
+    if (n >= 6 && magic[0] == 0xFD && !memcmp(magic + 1, "7zXZ", 4)) {
+      fclose(f);
+      err = path + ": xz-compressed input is not supported (kraken2 reads plain, gzip and bzip2)";
+      return false;
+    }
+    if (n >= 4 && magic[0] == 0x28 && magic[1] == 0xB5 && magic[2] == 0x2F && magic[3] == 0xFD) {
+      fclose(f);
+      err = path + ": zstd-compressed input is not supported (kraken2 reads plain, gzip and bzip2)";
+      return false;
+    }
     if (n >= 3 && magic[0] == 'B' && magic[1] == 'Z' && magic[2] == 'h') {
+      fclose(f);
       int fds[2];
       if (pipe2(fds, O_CLOEXEC)) {
         err = "pipe failed";
@@ -333,64 +451,133 @@ class InputStream {
       }
       ::close(in);
       ::close(fds[1]);
-      pipe_ = fdopen(fds[0], "rb");
-      return pipe_ != nullptr;
+      file_ = fdopen(fds[0], "rb");
+      if (!file_) {
+        ::close(fds[0]);
+        err = "cannot read from bzip2";
+        return false;
+      }
+      kind_ = 'b';
+    } else if (n >= 2 && magic[0] == 0x1f && magic[1] == 0x8b) {
+      file_ = f;
+      setvbuf(file_, nullptr, _IONBF, 0);
+      if (!gz_.begin(file_, magic, n)) {
+        err = "zlib initialisation failed";
+        return false;
+      }
+      kind_ = 'g';
+    } else {
+      file_ = f;
+      rewind(file_);
+      setvbuf(file_, nullptr, _IONBF, 0);
+      kind_ = 'u';
     }
-    if (n >= 6 && magic[0] == 0xFD && !memcmp(magic + 1, "7zXZ", 4)) {
-      err = path + ": xz-compressed input is not supported (kraken2 reads plain, gzip and bzip2)";
-      return false;
-    }
-    if (n >= 4 && magic[0] == 0x28 && magic[1] == 0xB5 && magic[2] == 0x2F && magic[3] == 0xFD) {
-      err = path + ": zstd-compressed input is not supported (kraken2 reads plain, gzip and bzip2)";
-      return false;
-    }
-    gz_ = gzopen(path.c_str(), "rb"); /* transparent for uncompressed files */
-    if (!gz_) {
-      err = "cannot open " + path;
-      return false;
-    }
-    gzbuffer(gz_, 1u << 20);
+    producer_ = std::thread([this] { produce(); });
     return true;
   }
-  /* returns bytes read, 0 at EOF, -1 on error */
-  long read(char *buf, size_t n) {
-    if (bgzf_) return bgzf_->read(buf, n);
-    if (gz_) {
-      int r = gzread(gz_, buf, (unsigned)n);
-      return r;
+  /* next run of decompressed bytes; returns its size, 0 at EOF, -1 on error */
+  long next(std::string &out) {
+    if (bgzf_) return bgzf_->next(out);
+    std::string *b = nullptr;
+    {
+      std::unique_lock<std::mutex> lk(m_);
+      cv_.wait(lk, [&] { return !ready_.empty() || finished_; });
+      if (ready_.empty()) return failed_ ? -1 : 0;
+      b = ready_.front();
+      ready_.pop_front();
     }
-    if (pipe_) {
-      size_t r = fread(buf, 1, n, pipe_);
-      if (r == 0 && ferror(pipe_)) return -1;
-      return (long)r;
+    out.swap(*b);
+    {
+      std::lock_guard<std::mutex> lk(m_);
+      free_.push_back(b);
+      cv_.notify_all();
     }
-    return -1;
+    return (long)out.size();
   }
   void close() {
-    bgzf_.reset();
-    if (gz_) gzclose(gz_), gz_ = nullptr;
-    if (pipe_) fclose(pipe_), pipe_ = nullptr;
-    if (pid_ > 0) {
-      int st;
-      waitpid(pid_, &st, 0);
-      pid_ = -1;
+    {
+      std::lock_guard<std::mutex> lk(m_);
+      stop_ = true;
+      cv_.notify_all();
     }
+    if (producer_.joinable()) producer_.join();
+    bgzf_.reset();
+    if (file_) fclose(file_), file_ = nullptr;
+    reap();
   }
 
  private:
+  static constexpr size_t BUF = 4u << 20;
+  static constexpr int NBUF = 4;
+  void reap() {
+    if (pid_ > 0) {
+      int st = 0;
+      waitpid(pid_, &st, 0);
+      pid_ = -1;
+      if (!(WIFEXITED(st) && WEXITSTATUS(st) == 0)) child_failed_ = true;
+    }
+  }
+  void produce() {
+    for (int i = 0; i < NBUF; i++) free_.push_back(&bufs_[i]);
+    bool bad = false;
+    for (;;) {
+      std::string *b = nullptr;
+      {
+        std::unique_lock<std::mutex> lk(m_);
+        cv_.wait(lk, [&] { return !free_.empty() || stop_; });
+        if (stop_) break;
+        b = free_.front();
+        free_.pop_front();
+      }
+      b->resize(BUF);
+      long n;
+      if (kind_ == 'g') {
+        n = gz_.read(&(*b)[0], BUF);
+      } else {
+        const size_t r = fread(&(*b)[0], 1, BUF, file_);
+        n = (r == 0 && ferror(file_)) ? -1 : (long)r;
+      }
+      if (n == 0 && kind_ == 'b') {
+        /* a truncated or corrupt .bz2 shows only in the exit status of the child */
+        fclose(file_), file_ = nullptr;
+        reap();
+        if (child_failed_) n = -1;
+      }
+      if (n <= 0) {
+        bad = n < 0;
+        break;
+      }
+      b->resize((size_t)n);
+      std::lock_guard<std::mutex> lk(m_);
+      ready_.push_back(b);
+      cv_.notify_all();
+    }
+    std::lock_guard<std::mutex> lk(m_);
+    failed_ = bad;
+    finished_ = true;
+    cv_.notify_all();
+  }
+
   std::unique_ptr<BgzfReader> bgzf_;
-  gzFile gz_ = nullptr;
-  FILE *pipe_ = nullptr;
+  GzipStream gz_;
+  FILE *file_ = nullptr;
+  int kind_ = 'u';
   pid_t pid_ = -1;
+  bool child_failed_ = false;
+  std::thread producer_;
+  std::mutex m_;
+  std::condition_variable cv_;
+  std::string bufs_[NBUF];
+  std::deque<std::string *> ready_, free_;
+  bool finished_ = false, failed_ = false, stop_ = false;
 };
 
 /* ------------------------------------------------------------------ */
 /* records                                                             */
 
 struct Rec {
-  uint32_t hdr_off, hdr_len;   /* full header line incl. '@' / '>' */
-  uint32_t seq_off, seq_len;
-  uint32_t qual_off, qual_len; /* FASTQ only */
+  size_t hdr_off, seq_off, qual_off; /* into Chunk::text; header = full line incl. '@' / '>'; quality FASTQ only */
+  uint32_t hdr_len, seq_len, qual_len;
 };
 
 struct Chunk {
@@ -406,19 +593,21 @@ class RecordReader {
  public:
   bool open(const std::string &path, int threads, std::string &err) {
     path_ = path;
-    buf_.resize(4u << 20);
     return in_.open(path, threads, err);
   }
-  /* fills `c` with up to NH_CHUNK_RECORDS records; c.last set at EOF */
-  void next_chunk(Chunk &c) {
+  /* Fills `c`; c.last set at EOF.  With want_records == 0 the reader cuts the chunk itself (records,
+   * bases or text bound); otherwise it reads exactly that many records (the second mate file follows
+   * the cuts of the first, so mates always sit in the same Work). */
+  void next_chunk(Chunk &c, size_t want_records = 0) {
     c.text.clear();
     c.recs.clear();
     c.bases = 0;
     c.error.clear();
     c.last = false;
     c.text.reserve(24u << 20);
-    c.recs.reserve(NH_CHUNK_RECORDS);
-    while (c.recs.size() < NH_CHUNK_RECORDS) {
+    c.recs.reserve(want_records ? want_records : NH_CHUNK_RECORDS);
+    const size_t max_records = want_records ? want_records : NH_CHUNK_RECORDS;
+    while (c.recs.size() < max_records) {
       if (format_ == 0) {
         int ch = peek();
         if (ch < 0) {
@@ -444,7 +633,7 @@ class RecordReader {
           c.last = true;
           break;
         }
-        r.hdr_off = (uint32_t)h0;
+        r.hdr_off = h0;
         r.hdr_len = (uint32_t)(t->size() - h0);
         if (r.hdr_len == 0) { /* kraken2 stops at an empty header line */
           t->resize(h0);
@@ -458,14 +647,14 @@ class RecordReader {
         }
         size_t s0 = t->size();
         getline_strip(*t);
-        r.seq_off = (uint32_t)s0;
+        r.seq_off = s0;
         r.seq_len = (uint32_t)(t->size() - s0);
         size_t p0 = t->size();
         getline_strip(*t); /* '+' line: dropped, kraken2 prints a bare '+' */
         t->resize(p0);
         size_t q0 = t->size();
         getline_strip(*t);
-        r.qual_off = (uint32_t)q0;
+        r.qual_off = q0;
         r.qual_len = (uint32_t)(t->size() - q0);
       } else {
         std::string *t = &c.text;
@@ -474,7 +663,7 @@ class RecordReader {
           c.last = true;
           break;
         }
-        r.hdr_off = (uint32_t)h0;
+        r.hdr_off = h0;
         r.hdr_len = (uint32_t)(t->size() - h0);
         if (r.hdr_len == 0) {
           t->resize(h0);
@@ -492,12 +681,17 @@ class RecordReader {
           if (ch < 0 || ch == '>') break;
           getline_strip(*t);
         }
-        r.seq_off = (uint32_t)s0;
+        r.seq_off = s0;
+        if (t->size() - s0 > 0x7FFFFFFFu) {
+          c.error = path_ + ": a sequence longer than 2^31 bases is not supported";
+          c.last = true;
+          break;
+        }
         r.seq_len = (uint32_t)(t->size() - s0);
       }
       c.bases += r.seq_len;
       c.recs.push_back(r);
-      if (c.text.size() > (3u << 30)) break; /* keep 32-bit offsets valid */
+      if (!want_records && (c.bases >= NH_CHUNK_BASES || c.text.size() >= NH_CHUNK_TEXT)) break;
     }
     if (io_error_) c.error = path_ + ": read error (truncated or corrupt compressed stream?)";
   }
@@ -505,7 +699,7 @@ class RecordReader {
  private:
   bool fill() {
     if (eof_) return false;
-    long n = in_.read(&buf_[0], buf_.size());
+    long n = in_.next(buf_);
     if (n < 0) {
       io_error_ = true;
       eof_ = true;
@@ -558,22 +752,48 @@ class RecordReader {
 /* output: ordered block compression                                    */
 
 typedef size_t (*zstd_bound_fn)(size_t);
-typedef size_t (*zstd_compress_fn)(void *, size_t, const void *, size_t, int);
 typedef unsigned (*zstd_iserror_fn)(size_t);
+typedef void *(*zstd_create_fn)(void);
+typedef size_t (*zstd_free_fn)(void *);
+typedef size_t (*zstd_setparam_fn)(void *, int, int);
+typedef size_t (*zstd_compress2_fn)(void *, void *, size_t, const void *, size_t);
 
+/* libzstd has no header in this image: the stable API is bound by hand (zstd.h, v1.4+) */
 struct ZstdLib {
+  static constexpr int C_COMPRESSION_LEVEL = 100, C_CHECKSUM_FLAG = 201; /* ZSTD_cParameter */
   void *h = nullptr;
   zstd_bound_fn bound = nullptr;
-  zstd_compress_fn compress = nullptr;
   zstd_iserror_fn is_error = nullptr;
+  zstd_create_fn create = nullptr;
+  zstd_free_fn free_ctx = nullptr;
+  zstd_setparam_fn set_param = nullptr;
+  zstd_compress2_fn compress2 = nullptr;
   bool load() {
     if (h) return true;
     h = dlopen("libzstd.so.1", RTLD_NOW);
     if (!h) return false;
     bound = (zstd_bound_fn)dlsym(h, "ZSTD_compressBound");
-    compress = (zstd_compress_fn)dlsym(h, "ZSTD_compress");
     is_error = (zstd_iserror_fn)dlsym(h, "ZSTD_isError");
-    return bound && compress && is_error;
+    create = (zstd_create_fn)dlsym(h, "ZSTD_createCCtx");
+    free_ctx = (zstd_free_fn)dlsym(h, "ZSTD_freeCCtx");
+    set_param = (zstd_setparam_fn)dlsym(h, "ZSTD_CCtx_setParameter");
+    compress2 = (zstd_compress2_fn)dlsym(h, "ZSTD_compress2");
+    return bound && is_error && create && free_ctx && set_param && compress2;
+  }
+  /* one frame per block, zstd's default level (3) with the content checksum the reference turns on
+   * (src/compression.rs:256-268: Encoder::new(out, 0) + include_checksum(true)) */
+  bool frame(const std::string &in, std::string &out) const {
+    void *cctx = create();
+    if (!cctx) return false;
+    bool ok = !is_error(set_param(cctx, C_COMPRESSION_LEVEL, 3)) && !is_error(set_param(cctx, C_CHECKSUM_FLAG, 1));
+    if (ok) {
+      out.resize(bound(in.size()));
+      const size_t n = compress2(cctx, &out[0], out.size(), in.data(), in.size());
+      ok = !is_error(n);
+      if (ok) out.resize(n);
+    }
+    free_ctx(cctx);
+    return ok;
   }
 };
 
@@ -623,32 +843,42 @@ static bool bgzf_members(const std::string &in, std::string &out) {
  * 'b' / 'x': piped through bzip2 / xz (their libraries have no headers here). */
 class OutputFile {
  public:
+  ~OutputFile() { close(); }
   bool open(const std::string &path, int format, int threads, std::string &err) {
     path_ = path;
     format_ = format;
     if (format == 'b' || format == 'x') {
+      /* the filter reads its stdin from a socket, not a pipe: send(MSG_NOSIGNAL) turns a filter that
+       * died early into an error return instead of a SIGPIPE that would kill the calling process */
       int out = ::open(path.c_str(), O_WRONLY | O_CREAT | O_TRUNC | O_CLOEXEC, 0644);
-      int fds[2];
-      if (out < 0 || pipe2(fds, O_CLOEXEC)) {
+      int fds[2] = {-1, -1};
+      if (out < 0 || socketpair(AF_UNIX, SOCK_STREAM | SOCK_CLOEXEC, 0, fds)) {
+        if (out >= 0) ::close(out);
         err = "cannot create " + path;
         return false;
       }
-      std::vector<std::string> av = format == 'b' ? std::vector<std::string>{"bzip2", "-c"}
-                                                  : std::vector<std::string>{"xz", "-c", "-6", "-T", std::to_string(threads < 1 ? 1 : threads)};
-      if (spawn_filter(av, fds[0], out, &pid_) != 0) {
+      /* bzip2 level 6 = bzip2::Compression::default() (src/compression.rs:203-212); xz preset 6 with
+       * the CLI's default CRC64 check, multi-threaded (src/compression.rs:236-254) */
+      std::vector<std::string> av = format == 'b' ? std::vector<std::string>{"bzip2", "-6", "-c"}
+                                                  : std::vector<std::string>{"xz", "-c", "-6", "--check=crc64", "-T",
+                                                                             std::to_string(threads < 1 ? 1 : threads)};
+      const int rc = spawn_filter(av, fds[0], out, &pid_);
+      ::close(out);
+      ::close(fds[0]);
+      if (rc != 0) {
+        ::close(fds[1]);
+        pid_ = -1;
         err = "cannot run " + av[0];
         return false;
       }
-      ::close(out);
-      ::close(fds[0]);
-      f_ = fdopen(fds[1], "wb");
-    } else {
-      if (format == 'z' && !zstd_.load()) {
-        err = "zstd output requested but libzstd.so.1 could not be loaded";
-        return false;
-      }
-      f_ = fopen(path.c_str(), "wb");
+      sock_ = fds[1];
+      return true;
     }
+    if (format == 'z' && !zstd_.load()) {
+      err = "zstd output requested but libzstd.so.1 could not be loaded";
+      return false;
+    }
+    f_ = fopen(path.c_str(), "wb");
     if (!f_) {
       err = "cannot create " + path;
       return false;
@@ -659,20 +889,30 @@ class OutputFile {
   bool parallel() const { return format_ == 'g' || format_ == 'z'; }
   bool compress_block(const std::string &in, std::string &out) {
     if (format_ == 'g') return bgzf_members(in, out);
-    if (format_ == 'z') {
-      out.resize(zstd_.bound(in.size()));
-      size_t n = zstd_.compress(&out[0], out.size(), in.data(), in.size(), 3);
-      if (zstd_.is_error(n)) return false;
-      out.resize(n);
-      return true;
-    }
+    if (format_ == 'z') return zstd_.frame(in, out);
     return false;
   }
-  bool write(const std::string &s) { return s.empty() || fwrite(s.data(), 1, s.size(), f_) == s.size(); }
+  bool write(const std::string &s) {
+    if (s.empty()) return true;
+    if (sock_ >= 0) {
+      size_t at = 0;
+      while (at < s.size()) {
+        const ssize_t n = send(sock_, s.data() + at, s.size() - at, MSG_NOSIGNAL);
+        if (n < 0) {
+          if (errno == EINTR) continue;
+          return false; /* EPIPE: the filter is gone */
+        }
+        at += (size_t)n;
+      }
+      return true;
+    }
+    return f_ && fwrite(s.data(), 1, s.size(), f_) == s.size();
+  }
   bool close() {
     bool ok = true;
     if (f_ && format_ == 'g') ok = fwrite(BGZF_EOF, 1, sizeof BGZF_EOF, f_) == sizeof BGZF_EOF; /* bgzip's end marker */
     if (f_) ok = (fclose(f_) == 0) && ok, f_ = nullptr;
+    if (sock_ >= 0) ::close(sock_), sock_ = -1; /* end of input for the filter */
     if (pid_ > 0) {
       int st = 0;
       waitpid(pid_, &st, 0);
@@ -687,6 +927,7 @@ class OutputFile {
   std::string path_;
   int format_ = 'u';
   FILE *f_ = nullptr;
+  int sock_ = -1;
   pid_t pid_ = -1;
   ZstdLib zstd_;
 };
@@ -915,7 +1156,7 @@ static bool write_report(const char *path, const nh_db *db, const std::vector<ui
   if (!f) return false;
   const size_t n = db->h_parent.size();
   std::vector<uint64_t> clade(call_counts);
-  for (size_t i = n - 1; i >= 2; i--) clade[db->h_parent[i]] += clade[i]; /* parent id < child id */
+  for (size_t i = n; i-- > 2;) clade[db->h_parent[i]] += clade[i]; /* parent id < child id */
   std::vector<std::vector<uint32_t>> kids(n);
   for (size_t i = 2; i < n; i++) kids[db->h_parent[i]].push_back((uint32_t)i);
   auto line = [&](uint64_t cl, uint64_t direct, const std::string &rank, uint64_t taxid, const std::string &name, int depth) {
@@ -966,7 +1207,15 @@ static int run_pipeline(const Decider &dec, const nh_files_t *files, nh_run_stat
   const bool want_report = files->kraken_report != nullptr;
   if ((want_lines || want_report) && dec.dbs.empty())
     return nh_set_error(NH_ERR_UNSUPPORTED, "kraken output / report need the database (not available to the rewrite hook)");
+  int fmt = files->out_format ? files->out_format : 'u';
+  if (!strchr("ugbxz", fmt)) return nh_set_error(NH_ERR_INVALID, "unknown output format '%c'", fmt);
   FILE *kout = nullptr;
+  struct Closer { /* every early return below closes the per-read output */
+    FILE *&f;
+    ~Closer() {
+      if (f) fclose(f);
+    }
+  } kout_closer{kout};
   if (want_lines) {
     kout = fopen(files->kraken_output, "w");
     if (!kout) return nh_set_error(NH_ERR_IO, "cannot create %s", files->kraken_output);
@@ -981,8 +1230,6 @@ static int run_pipeline(const Decider &dec, const nh_files_t *files, nh_run_stat
   }
   const int db_k = dec.dbs.empty() ? 0 : (int)dec.dbs[0]->info.k;
   const int db_amb_span = dec.dbs.empty() ? 0 : dec.dbs[0]->params.amb_span;
-  int fmt = files->out_format ? files->out_format : 'u';
-  if (!strchr("ugbxz", fmt)) return nh_set_error(NH_ERR_INVALID, "unknown output format '%c'", fmt);
   const int threads = dec.params.threads < 1 ? 1 : dec.params.threads;
   const bool keep_human = dec.params.keep_human != 0;
 
@@ -1002,15 +1249,34 @@ static int run_pipeline(const Decider &dec, const nh_files_t *files, nh_run_stat
   /* readers */
   Channel<std::unique_ptr<Chunk>> chunks[2] = {Channel<std::unique_ptr<Chunk>>(3), Channel<std::unique_ptr<Chunk>>(3)};
   std::vector<std::thread> reader_threads;
+  /* the first file's reader decides where chunks end; the second mate file reads the same number of
+   * records, so a pair never straddles two Works whatever the read lengths are */
+  struct Cut {
+    size_t records;
+    bool last;
+  };
+  Channel<Cut> cuts(64);
   for (int f = 0; f < nf; f++)
     reader_threads.emplace_back([&, f] {
       for (;;) {
         auto c = std::make_unique<Chunk>();
-        readers[f].next_chunk(*c);
+        if (f == 0) {
+          readers[0].next_chunk(*c);
+          if (paired && !cuts.push(Cut{c->recs.size(), c->last})) c->last = true;
+        } else {
+          Cut cut{0, true};
+          if (!cuts.pop(cut)) cut = Cut{0, true};
+          if (cut.records)
+            readers[1].next_chunk(*c, cut.records);
+          else
+            c->fastq = true;
+          if (cut.last) c->last = true; /* nothing of this file is needed beyond the end of the first */
+        }
         bool last = c->last;
         if (!chunks[f].push(std::move(c)) || last) break;
       }
       chunks[f].close();
+      if (f == 0) cuts.close();
     });
 
   /* classifiers */
@@ -1055,8 +1321,10 @@ static int run_pipeline(const Decider &dec, const nh_files_t *files, nh_run_stat
       input_done = true;
     }
     w->id = next_id++;
-    if (input_done)
+    if (input_done) {
       for (int f = 0; f < nf; f++) chunks[f].close();
+      cuts.close();
+    }
     return w;
   };
 
@@ -1091,44 +1359,73 @@ static int run_pipeline(const Decider &dec, const nh_files_t *files, nh_run_stat
               fixed_cursor += w->n_units;
             }
           } else {
-            if (total + 64 > cap_bases || n_seqs + 1 > cap_seqs) {
-              /* (re)size the session and its pinned staging buffers for this chunk shape */
+            /* A Work goes to the GPU in sub-batches of at most cap_bases bases: the session keeps one
+             * size whatever the read lengths are (ultra-long ONT, FASTA contigs) and only grows when a
+             * single unit is longer than it. */
+            uint64_t longest = 0;
+            for (uint64_t i = 0; i < w->n_units; i++) {
+              uint64_t ub = 0;
+              for (int f = 0; f < nf; f++) ub += w->c[f].recs[i].seq_len;
+              longest = std::max(longest, ub);
+            }
+            const uint64_t want_cap = std::max<uint64_t>(NH_BATCH_BASES, longest + 64);
+            if (!sess || want_cap > cap_bases) {
               if (sess) nh_session_destroy(sess), sess = nullptr;
               if (h_bases) nh_host_free(h_bases), h_bases = nullptr;
               if (h_off) nh_host_free(h_off), h_off = nullptr;
-              cap_bases = (size_t)(total + total / 4) + (1u << 20);
+              cap_bases = (size_t)want_cap;
               cap_seqs = (size_t)NH_CHUNK_RECORDS * nf + 2;
               nh_params_t p = dec.params;
               p.max_batch_bases = cap_bases;
               p.max_batch_seqs = cap_seqs;
               p.emit_runs = want_lines ? 1 : 0;
-              h_bases = (uint8_t *)nh_host_alloc(cap_bases);
-              h_off = (uint64_t *)nh_host_alloc(cap_seqs * 8);
-              if (!h_bases || !h_off || nh_session_create(dec.dbs[(size_t)ci % dec.dbs.size()], &p, &sess) != NH_OK) {
-                w->error = std::string("cannot set up a GPU session: ") + nh_last_error();
-                sess = nullptr;
+              if (cap_bases > (1ull << 31))
+                w->error = "a single read (pair) of more than 2^31 bases is not supported";
+              else {
+                h_bases = (uint8_t *)nh_host_alloc(cap_bases);
+                h_off = (uint64_t *)nh_host_alloc(cap_seqs * 8);
+                if (!h_bases || !h_off || nh_session_create(dec.dbs[(size_t)ci % dec.dbs.size()], &p, &sess) != NH_OK) {
+                  w->error = std::string("cannot set up a GPU session: ") + nh_last_error();
+                  if (sess) nh_session_destroy(sess);
+                  sess = nullptr;
+                  cap_bases = 0;
+                }
               }
             }
-            if (w->error.empty()) {
-              uint64_t o = 0, s = 0;
-              for (uint64_t i = 0; i < w->n_units; i++)
+            if (want_lines && w->error.empty()) {
+              w->first_run.assign(n_seqs + 1, 0);
+              w->run_ext.resize(total + 1);
+              w->run_len.resize(total + 1);
+            }
+            uint64_t u0 = 0, runs_at = 0;
+            while (w->error.empty() && u0 < w->n_units) {
+              uint64_t o = 0, s = 0, u1 = u0;
+              for (; u1 < w->n_units; u1++) {
+                uint64_t ub = 0;
+                for (int f = 0; f < nf; f++) ub += w->c[f].recs[u1].seq_len;
+                if (u1 > u0 && o + ub + 64 > cap_bases) break;
                 for (int f = 0; f < nf; f++) { /* mates interleaved: sequences 2i, 2i+1 */
-                  const Rec &r = w->c[f].recs[i];
+                  const Rec &r = w->c[f].recs[u1];
                   h_off[s++] = o;
                   memcpy(h_bases + o, w->c[f].text.data() + r.seq_off, r.seq_len);
                   o += r.seq_len;
                 }
+              }
               h_off[s] = o;
-              if (nh_classify_batch(sess, h_bases, h_off, n_seqs, w->call.data(), w->keep.data(), nullptr) != NH_OK)
+              if (nh_classify_batch(sess, h_bases, h_off, s, w->call.data() + u0, w->keep.data() + u0, nullptr) != NH_OK)
                 w->error = std::string("classification failed: ") + nh_last_error();
               if (want_lines && w->error.empty()) {
-                w->first_run.resize(n_seqs + 1);
-                w->run_ext.resize(total + 1);
-                w->run_len.resize(total + 1);
                 uint64_t nr = 0;
-                if (nh_last_batch_runs(sess, n_seqs, w->first_run.data(), w->run_ext.data(), w->run_len.data(), total + 1, &nr) != NH_OK)
+                uint32_t *fr = w->first_run.data() + u0 * nf;
+                if (nh_last_batch_runs(sess, s, fr, w->run_ext.data() + runs_at, w->run_len.data() + runs_at,
+                                       total + 1 - runs_at, &nr) != NH_OK)
                   w->error = std::string("reading the hit runs failed: ") + nh_last_error();
+                else {
+                  for (uint64_t j = 0; j <= s; j++) fr[j] += (uint32_t)runs_at; /* fr[s] is the next sub-batch's first entry */
+                  runs_at += nr;
+                }
               }
+              u0 = u1;
             }
           }
         }
@@ -1223,14 +1520,19 @@ static int run_pipeline(const Decider &dec, const nh_files_t *files, nh_run_stat
   }
   for (int f = 0; f < nf; f++) bw.submit(f, std::move(pend[f]));
   for (int f = 0; f < nf; f++) chunks[f].close();
+  cuts.close();
   for (auto &t : classifier_threads) t.join();
   for (auto &t : reader_threads) t.join();
   bool wrote = bw.finish();
   for (int f = 0; f < nf; f++) wrote = outs[f].close() && wrote;
   (void)keep_human;
-  if (kout && fclose(kout) != 0 && !failed) {
-    failed = true;
-    fail_msg = std::string("writing ") + files->kraken_output + " failed";
+  if (kout) {
+    const bool closed_ok = fclose(kout) == 0;
+    kout = nullptr;
+    if (!closed_ok && !failed) {
+      failed = true;
+      fail_msg = std::string("writing ") + files->kraken_output + " failed";
+    }
   }
   if (want_report && !failed &&
       !write_report(files->kraken_report, dec.dbs[0], call_counts, total_units, total_units - n_classified)) {

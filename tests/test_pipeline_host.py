@@ -258,3 +258,113 @@ def test_gzip_output_is_bgzf_and_is_read_back_in_parallel(tmp_path):
     b1.write_bytes(bytes(bad))
     with pytest.raises(NhError):
         rewrite_files(keep, call, b1, tmp_path / "x1.fq", g2, tmp_path / "x2.fq", threads=8)
+
+
+def test_truncated_compressed_input_is_an_error(tmp_path):
+    """A .fq.gz / .fq.bz2 / blocked .gz cut in the middle must fail the run (zlib's gzread hands back the
+    bytes it has and only sets Z_BUF_ERROR; kraken2 + the reference would silently drop the rest)."""
+    n = 20000
+    recs = make_records(n, seed=21)
+    keep, call = np.ones(n, np.uint8), np.zeros(n, np.uint32)
+    plain = tmp_path / "t.fq"
+    write_input(plain, recs)
+    raw = open(plain, "rb").read()
+    for name, data in (("t.fq.gz", gzip.compress(raw)), ("t.fq.bz2", bz2.compress(raw))):
+        whole = tmp_path / name
+        whole.write_bytes(data)
+        st = rewrite_files(keep, call, whole, tmp_path / "ok.fq", threads=4)
+        assert st.total == n
+        cut = tmp_path / ("cut_" + name)
+        cut.write_bytes(data[:len(data) // 2])
+        with pytest.raises(NhError) as ei:
+            rewrite_files(keep, call, cut, tmp_path / "o.fq", threads=4)
+        assert "truncated or corrupt" in ei.value.message
+    # blocked gzip, cut inside a member and between members
+    bg = tmp_path / "t.bgz.gz"
+    rewrite_files(keep, call, plain, bg, out_format="g", threads=4)
+    data = open(bg, "rb").read()
+    cut = tmp_path / "cut.bgz.gz"
+    cut.write_bytes(data[:len(data) // 2])
+    with pytest.raises(NhError):
+        rewrite_files(keep, call, cut, tmp_path / "o.fq", threads=4)
+    # a gzip stream with trailing garbage after a complete member is read like gzread reads it
+    tg = tmp_path / "garbage.fq.gz"
+    tg.write_bytes(gzip.compress(raw) + b"\x00" * 100)
+    assert rewrite_files(keep, call, tg, tmp_path / "o2.fq", threads=1).total == n
+    # concatenated members (cat a.gz b.gz)
+    half = raw.index(b"\n@read10000 ") + 1
+    cat = tmp_path / "cat.fq.gz"
+    cat.write_bytes(gzip.compress(raw[:half]) + gzip.compress(raw[half:]))
+    assert rewrite_files(keep, call, cat, tmp_path / "o3.fq", threads=1).total == n
+    assert open(tmp_path / "o3.fq", "rb").read() == expected(recs, keep, call)
+
+
+def test_blocked_gzip_followed_by_plain_members(tmp_path):
+    """`cat blocked.gz plain.gz`: the first member selects the parallel reader, later members have no BC
+    subfield; zlib and kraken2 read such a file, so must we.  A member announcing more than 64 KiB is refused."""
+    import struct
+    n = 6000
+    recs = make_records(n, seed=22)
+    keep, call = np.ones(n, np.uint8), np.zeros(n, np.uint32)
+    plain = tmp_path / "m.fq"
+    write_input(plain, recs)
+    raw = open(plain, "rb").read()
+    half = raw.index(b"\n@read3000 ") + 1
+    (tmp_path / "h1.fq").write_bytes(raw[:half])
+    rewrite_files(keep, call, tmp_path / "h1.fq", tmp_path / "h1.gz", out_format="g", threads=2)
+    blocked = open(tmp_path / "h1.gz", "rb").read()
+    blocked = blocked[:-28]  # without bgzip's empty end marker
+    mixed = tmp_path / "mixed.fq.gz"
+    mixed.write_bytes(blocked + gzip.compress(raw[half:]))
+    st = rewrite_files(keep, call, mixed, tmp_path / "o.fq", threads=4)
+    assert st.total == n and open(tmp_path / "o.fq", "rb").read() == expected(recs, keep, call)
+    # forged ISIZE: a member that claims 1 GiB
+    forged = bytearray(blocked)
+    bsize = struct.unpack_from("<H", forged, 16)[0] + 1
+    struct.pack_into("<I", forged, bsize - 4, 1 << 30)
+    bad = tmp_path / "forged.fq.gz"
+    bad.write_bytes(bytes(forged))
+    with pytest.raises(NhError):
+        rewrite_files(keep, call, bad, tmp_path / "o2.fq", threads=4)
+
+
+def test_codec_parameters_follow_the_reference(tmp_path):
+    """src/compression.rs:203-212 bzip2 level default (6), :256-268 zstd frames carry the content checksum."""
+    n = 3000
+    recs = make_records(n, seed=23)
+    keep, call = np.ones(n, np.uint8), np.zeros(n, np.uint32)
+    inp = tmp_path / "c.fq"
+    write_input(inp, recs)
+    if shutil.which("bzip2"):
+        rewrite_files(keep, call, inp, tmp_path / "o.bz2", out_format="b")
+        assert open(tmp_path / "o.bz2", "rb").read(4) == b"BZh6"
+    rewrite_files(keep, call, inp, tmp_path / "o.zst", out_format="z", threads=2)
+    raw = open(tmp_path / "o.zst", "rb").read()
+    assert raw[:4] == b"\x28\xb5\x2f\xfd"
+    assert raw[4] & 0x04, "Content_Checksum_flag of the frame header descriptor"
+    assert read_output(tmp_path / "o.zst", "z") == expected(recs, keep, call)
+
+
+def test_long_reads_cut_chunks_by_bases_and_mates_stay_together(tmp_path):
+    """Chunks end after 65536 records OR ~48 Mbp of the first file; the second file follows the first
+    file's cuts, so pairs stay aligned when the mates' lengths differ wildly."""
+    rng = np.random.default_rng(24)
+    n = 130
+    r1, r2 = [], []
+    for i in range(n):
+        L1 = int(rng.integers(400_000, 1_200_000))  # ~100 Mbp in total: several chunks
+        L2 = int(rng.integers(1, 300))
+        s1 = bytes(synth.random_genome(rng, L1))
+        s2 = bytes(synth.random_genome(rng, L2))
+        r1.append((f"@long{i}/1".encode(), s1, b"I" * L1))
+        r2.append((f"@long{i}/2".encode(), s2, b"J" * L2))
+    i1, i2 = tmp_path / "l_1.fq", tmp_path / "l_2.fq"
+    write_input(i1, r1)
+    write_input(i2, r2)
+    keep = (np.arange(n) % 3 != 0).astype(np.uint8)
+    call = np.where(keep == 0, 9606, 0).astype(np.uint32)
+    o1, o2 = tmp_path / "o_1.fq", tmp_path / "o_2.fq"
+    st = rewrite_files(keep, call, i1, o1, i2, o2, threads=2)
+    assert st.total == n
+    assert open(o1, "rb").read() == expected(r1, keep, call)
+    assert open(o2, "rb").read() == expected(r2, keep, call)
