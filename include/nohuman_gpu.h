@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define NH_ABI_VERSION 1
+#define NH_ABI_VERSION 2
 
 typedef enum {
   NH_OK = 0,
@@ -159,7 +159,7 @@ int nh_session_sync(nh_session *s, nh_batch_stats_t *stats);
  * vector (classify.cc) without its ambiguous entries, which the host derives
  * from the sequence itself.  Host pointers; *n_runs gets the total. */
 int nh_last_batch_runs(nh_session *s, uint64_t n_seqs, uint32_t *seq_first_run, uint32_t *run_taxon_ext,
-                       uint8_t *run_len, uint64_t run_capacity, uint64_t *n_runs);
+                       uint16_t *run_len, uint64_t run_capacity, uint64_t *n_runs);
 /* The CUDA stream (cudaStream_t) the session launches on. */
 void *nh_session_stream(nh_session *s);
 

@@ -175,7 +175,7 @@ class Session:
         """(seq_first_run[n_seqs+1], run_taxon_ext, run_len) of the batch just classified."""
         first = np.zeros(n_seqs + 1, np.uint32)
         ext = np.zeros(max(capacity, 1), np.uint32)
-        ln = np.zeros(max(capacity, 1), np.uint8)
+        ln = np.zeros(max(capacity, 1), np.uint16)
         n = C.c_uint64()
         check(lib().nh_last_batch_runs(self._h, n_seqs, first.ctypes.data, ext.ctypes.data, ln.ctypes.data,
                                        capacity, C.byref(n)))

@@ -13,6 +13,7 @@
 #include <string.h>
 #include <sys/stat.h>
 
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -188,6 +189,7 @@ static int finish_db(nh_db *db, const uint64_t hdr[4]) {
   P.l = (int32_t)I.l;
   P.w = P.k - P.l + 1;
   P.tile_pos = NH_TILE_LMERS - (P.w - 1);
+  P.legacy_tile_pos = P.tile_pos;
   P.amb_span = P.l > P.k - 1 ? P.l : P.k - 1;
   P.revcom_version = I.revcom_version;
   const uint64_t lmer_mask = (1ULL << (2 * I.l)) - 1;
@@ -461,7 +463,10 @@ static cudaError_t dmalloc(T **p, size_t n) {
   return cudaMalloc((void **)p, n * sizeof(T));
 }
 
-extern "C" int nh_session_create(nh_db *db, const nh_params_t *params, nh_session **out) {
+/* need_lookups: also allocate the per-lookup scratch of the warp-per-tile kernels (8 + 2 + 4 bytes
+ * per base).  The streaming kernel keeps its lookups in shared memory, so ordinary sessions only
+ * carry 2 + 4 bytes per base when the caller asked for per-read hit runs (emit_runs). */
+int nh_session_create_ex(nh_db *db, const nh_params_t *params, bool need_lookups, nh_session **out) {
   if (!db || !params || !out) return nh_set_error(NH_ERR_INVALID, "null argument");
   if (!(params->confidence >= 0.0 && params->confidence <= 1.0))
     return nh_set_error(NH_ERR_INVALID, "Confidence score must be between 0 and 1");
@@ -482,31 +487,29 @@ extern "C" int nh_session_create(nh_db *db, const nh_params_t *params, nh_sessio
   s->cap_bases = mb;
   s->cap_seqs = ms;
   {
-    /* NH_LEGACY_KERNELS=1 forces the warp-per-tile kernels (A/B runs, generic window widths) */
+    /* NH_LEGACY_KERNELS=1 forces the warp-per-tile kernels (A/B runs; databases whose window is not 5 take them anyway) */
     const char *legacy = getenv("NH_LEGACY_KERNELS");
     s->use_fused = nh_fused_supported(db->params) && !(legacy && legacy[0] == '1');
     /* NH_TEST_LANE_TAXA=n shrinks the in-warp taxon table so tests reach the overflow pass */
-    const char *form = getenv("NH_FUSED_KERNEL");
-    s->fused_form = form && !strcmp(form, "phased") ? 1 : 2;
     const char *lt = getenv("NH_TEST_LANE_TAXA");
     int v = lt ? atoi(lt) : NH_LANE_TAXA;
     s->lane_taxa = v < 1 ? 1 : (v > NH_LANE_TAXA ? NH_LANE_TAXA : v);
-  }
-  /* The session works on its own copy of the constants: the lane-serial fused kernel takes
-   * tiles of up to NH_FUSED_TILE_POS k-mer positions (u8 run lengths cap them at 255); longer
-   * tiles make 250 bp reads single-tile units and halve the (k-1)-base overlap long reads pay. */
-  s->P = db->params;
-  if (s->use_fused) {
+    /* NH_FUSED_TILE_POS=n fixes the tile size of the streaming kernel (default: by mean read length) */
     const char *tp = getenv("NH_FUSED_TILE_POS");
-    int v = tp ? atoi(tp) : NH_FUSED_TILE_POS;
-    s->P.tile_pos = v < 16 ? 16 : (v > 255 ? 255 : v);
+    s->forced_tile_pos = tp ? atoi(tp) : 0;
+    if (s->forced_tile_pos && s->forced_tile_pos < 16) s->forced_tile_pos = 16;
+    if (s->forced_tile_pos > NH_FUSED_TILE_POS_MAX) s->forced_tile_pos = NH_FUSED_TILE_POS_MAX;
   }
+  s->P = db->params; /* the session's own copy: enqueue_batch sets the tile size per batch */
   const NhDbParams &P = s->P;
-  /* every sequence has at most ceil(positions / tile_pos) tiles; sized for the smaller
-   * (warp-per-tile) tiles, which the synthetic builder uses on this session's buffers */
-  s->cap_tiles = ms + mb / (uint64_t)(P.tile_pos < db->params.tile_pos ? P.tile_pos : db->params.tile_pos) + 1;
-  /* one lookup per k-mer position at most */
-  s->cap_lookups = mb;
+  /* every sequence has at most ceil(positions / tile_pos) tiles; sized for the smallest tile any
+   * kernel of this session may use */
+  int min_tile = db->params.tile_pos < NH_FUSED_TILE_POS_LONG ? db->params.tile_pos : NH_FUSED_TILE_POS_LONG;
+  if (s->forced_tile_pos && s->forced_tile_pos < min_tile) min_tile = s->forced_tile_pos;
+  if (!s->use_fused || need_lookups) min_tile = std::min(min_tile, (int)db->params.tile_pos);
+  s->cap_tiles = ms + mb / (uint64_t)min_tile + 1;
+  s->cap_lookups = mb; /* one lookup per k-mer position at most */
+  const bool want_lookups = need_lookups || !s->use_fused;
   cudaError_t e = cudaSuccess;
 #define ALLOC(ptr, n)                                     \
   if (e == cudaSuccess) e = dmalloc(&(ptr), (size_t)(n)); \
@@ -517,9 +520,13 @@ extern "C" int nh_session_create(nh_db *db, const nh_params_t *params, nh_sessio
   ALLOC(s->d_block_sums, ms / 1024 + 2);
   ALLOC(s->d_tiles, s->cap_tiles);
   ALLOC(s->d_tile_out, s->cap_tiles);
-  ALLOC(s->d_lk_min, s->cap_lookups);
-  ALLOC(s->d_lk_cnt, s->cap_lookups);
-  ALLOC(s->d_lk_taxon, s->cap_lookups);
+  if (want_lookups) {
+    ALLOC(s->d_lk_min, s->cap_lookups);
+  }
+  if (want_lookups || params->emit_runs) {
+    ALLOC(s->d_lk_cnt, s->cap_lookups);
+    ALLOC(s->d_lk_taxon, s->cap_lookups);
+  }
   ALLOC(s->d_out_call, ms);
   ALLOC(s->d_out_keep, ms);
   ALLOC(s->d_dbg_call, ms);
@@ -528,7 +535,7 @@ extern "C" int nh_session_create(nh_db *db, const nh_params_t *params, nh_sessio
   ALLOC(s->d_overflow, ms);
   ALLOC(s->d_deferred, ms);
   ALLOC(s->d_counters, 1);
-  if (s->use_fused && s->fused_form == 2) {
+  if (s->use_fused) {
     ALLOC(s->d_tile_tab, s->cap_tiles);
     ALLOC(s->d_tile_sum, s->cap_tiles);
   }
@@ -550,8 +557,13 @@ extern "C" int nh_session_create(nh_db *db, const nh_params_t *params, nh_sessio
     return rc;
   }
   memset(s->h_counters, 0, sizeof(NhCounters));
+  (void)P;
   *out = s;
   return NH_OK;
+}
+
+extern "C" int nh_session_create(nh_db *db, const nh_params_t *params, nh_session **out) {
+  return nh_session_create_ex(db, params, false, out);
 }
 
 extern "C" void nh_session_destroy(nh_session *s) {
@@ -609,6 +621,13 @@ static int enqueue_batch(nh_session *s, const uint8_t *d_bases, const uint64_t *
                          uint64_t n_seqs, uint64_t total_bases, uint32_t *d_out_call,
                          uint8_t *d_out_keep, bool with_debug, const uint64_t *d_pos_off,
                          uint64_t *d_pos_min, uint8_t *d_pos_amb) {
+  /* Tile size of the streaming kernel: 508 positions keep every short read (2x300 bp included) in
+   * one tile; batches of long reads take 252, which doubles the number of 32-tile groups the
+   * persistent warps draw from (better balance) at 7 % more overlap scanned. */
+  if (s->use_fused) {
+    const uint64_t mean_len = n_seqs ? total_bases / n_seqs : 0;
+    s->P.tile_pos = s->forced_tile_pos ? s->forced_tile_pos : (mean_len > 1000 ? NH_FUSED_TILE_POS_LONG : NH_FUSED_TILE_POS);
+  }
   const NhDbParams &P = s->P;
   NhBatchPtrs B;
   memset(&B, 0, sizeof B);
@@ -649,18 +668,16 @@ static int enqueue_batch(nh_session *s, const uint8_t *d_bases, const uint64_t *
   cudaEventRecord(s->ev[EV_PLAN0], st);
   const bool fused = s->use_fused;
   B.deferred_units = fused ? s->d_deferred : nullptr;
-  B.emit_all_taxa = s->params.emit_runs ? 1 : 0;
+  const bool emit = s->params.emit_runs && d_pos_min == nullptr;
+  B.emit_all_taxa = emit ? 1 : 0;
   launches += nh_launch_plan(P, B, st);
   cudaEventRecord(s->ev[EV_MIN0], st);
   if (fused) {
-    /* scan + probe + in-warp scoring of short units in one kernel; ms_probe reads 0 */
-    /* NH_FUSED_KERNEL=stream|phased picks the form of the fused kernel (default: streaming) */
-    s->last_form = s->fused_form;
-    if (s->last_form == 2) {
-      B.tile_tab = s->d_tile_tab;
-      B.tile_sum = s->d_tile_sum;
-    }
-    launches += nh_launch_fused(P, B, SP, (uint32_t)tiles_upper, sm, s->last_form, st);
+    /* scan + probe + in-warp scoring in one kernel; ms_probe reads 0 */
+    s->last_form = 2;
+    B.tile_tab = s->d_tile_tab;
+    B.tile_sum = s->d_tile_sum;
+    launches += nh_launch_stream(P, B, SP, (uint32_t)tiles_upper, sm, st);
     cudaEventRecord(s->ev[EV_PROBE0], st);
   } else {
     launches += nh_launch_minimizers(P, B, (uint32_t)tiles_upper, sm, st);
@@ -670,7 +687,7 @@ static int enqueue_batch(nh_session *s, const uint8_t *d_bases, const uint64_t *
   }
   cudaEventRecord(s->ev[EV_SCORE0], st);
   launches += nh_launch_score(P, B, SP, sm, st);
-  if (s->params.emit_runs)
+  if (emit)
     launches += nh_launch_gather_runs(P, B, (uint32_t)tiles_upper, s->d_run_ext, s->d_run_len, s->d_tile_run_off,
                                       s->d_run_cursor, sm, st);
   cudaEventRecord(s->ev[EV_SCORE1], st);
@@ -853,7 +870,7 @@ extern "C" int nh_debug_last_batch(nh_session *s, uint32_t *out_call_internal,
 }
 
 extern "C" int nh_last_batch_runs(nh_session *s, uint64_t n_seqs, uint32_t *seq_first_run,
-                                  uint32_t *run_taxon_ext, uint8_t *run_len, uint64_t run_capacity,
+                                  uint32_t *run_taxon_ext, uint16_t *run_len, uint64_t run_capacity,
                                   uint64_t *n_runs) {
   if (!s || !seq_first_run || !run_taxon_ext || !run_len) return nh_set_error(NH_ERR_INVALID, "null argument");
   if (!s->params.emit_runs) return nh_set_error(NH_ERR_INVALID, "session was not created with emit_runs");
@@ -867,7 +884,7 @@ extern "C" int nh_last_batch_runs(nh_session *s, uint64_t n_seqs, uint32_t *seq_
   if (total > run_capacity) return nh_set_error(NH_ERR_CAPACITY, "%u runs do not fit the caller's %llu", total, (unsigned long long)run_capacity);
   std::vector<uint32_t> tile_base(n_seqs + 1), tile_off(n_tiles), ext(total);
   std::vector<NhTileOut> tile_out(n_tiles);
-  std::vector<uint8_t> len(total);
+  std::vector<uint16_t> len(total);
   CUDA_TRY(cudaMemcpy(tile_base.data(), s->d_tile_base, (n_seqs + 1) * 4, cudaMemcpyDeviceToHost));
   if (n_tiles) {
     CUDA_TRY(cudaMemcpy(tile_off.data(), s->d_tile_run_off, (size_t)n_tiles * 4, cudaMemcpyDeviceToHost));
@@ -875,7 +892,7 @@ extern "C" int nh_last_batch_runs(nh_session *s, uint64_t n_seqs, uint32_t *seq_
   }
   if (total) {
     CUDA_TRY(cudaMemcpy(ext.data(), s->d_run_ext, (size_t)total * 4, cudaMemcpyDeviceToHost));
-    CUDA_TRY(cudaMemcpy(len.data(), s->d_run_len, total, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(len.data(), s->d_run_len, (size_t)total * 2, cudaMemcpyDeviceToHost));
   }
   /* tiles were packed in completion order; hand the runs back in sequence order */
   uint32_t o = 0;
@@ -884,7 +901,7 @@ extern "C" int nh_last_batch_runs(nh_session *s, uint64_t n_seqs, uint32_t *seq_
     for (uint32_t t = tile_base[i]; t < tile_base[i + 1]; t++) {
       const uint32_t n = tile_out[t].lk_cnt, from = tile_off[t];
       memcpy(run_taxon_ext + o, ext.data() + from, (size_t)n * 4);
-      memcpy(run_len + o, len.data() + from, n);
+      memcpy(run_len + o, len.data() + from, (size_t)n * 2);
       o += n;
     }
   }

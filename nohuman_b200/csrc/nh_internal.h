@@ -48,7 +48,7 @@ struct nh_session {
   NhTile *d_tiles = nullptr;
   NhTileOut *d_tile_out = nullptr;
   uint64_t *d_lk_min = nullptr;
-  uint8_t *d_lk_cnt = nullptr;
+  uint16_t *d_lk_cnt = nullptr;
   uint32_t *d_lk_taxon = nullptr;
   uint32_t *d_out_call = nullptr;
   uint8_t *d_out_keep = nullptr;
@@ -56,11 +56,12 @@ struct nh_session {
   uint32_t *d_overflow = nullptr;
   uint32_t *d_deferred = nullptr;
   uint32_t *d_run_ext = nullptr, *d_tile_run_off = nullptr, *d_run_cursor = nullptr;
-  uint8_t *d_run_len = nullptr;
+  uint16_t *d_run_len = nullptr;
   uint64_t last_seqs = 0;
   bool use_fused = false, last_fused = false;
   int lane_taxa = NH_LANE_TAXA;
-  int last_form = 0, fused_form = 2; /* 1: k_scan_probe_score, 2: k_stream_classify */
+  int last_form = 0;       /* 0: warp-per-tile kernels, 2: k_stream_classify */
+  int forced_tile_pos = 0; /* NH_FUSED_TILE_POS */
   NhTileTab *d_tile_tab = nullptr;
   NhTileSum *d_tile_sum = nullptr;
   NhCounters *d_counters = nullptr;
@@ -74,6 +75,7 @@ struct nh_session {
 };
 
 int nh_set_error(int code, const char *fmt, ...);
+int nh_session_create_ex(nh_db *db, const nh_params_t *params, bool need_lookups, nh_session **out);
 int nh_resolve_db_dir(const char *db_dir, std::string &out);
 
 #endif

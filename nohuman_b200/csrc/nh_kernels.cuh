@@ -15,7 +15,9 @@
 #endif
 #define NH_BLOCK_THREADS (NH_WARPS_PER_BLOCK * 32)
 #define NH_TILE_LMERS 128           /* l-mers per minimizer tile of the warp-per-tile kernel (4 warp iterations) */
-#define NH_FUSED_TILE_POS 252       /* k-mer positions per tile of the lane-serial fused kernel (<= 255) */
+#define NH_FUSED_TILE_POS 508       /* k-mer positions per tile of the lane-serial kernel: 2x300 bp reads stay one tile */
+#define NH_FUSED_TILE_POS_LONG 252  /* ... for batches of long reads: more, smaller groups balance better */
+#define NH_FUSED_TILE_POS_MAX 1023  /* run lengths travel in 10 bits */
 #define NH_MAX_WINDOW 32            /* k - l + 1 must fit one warp */
 #define NH_SMEM_PARENT_MAX 8192     /* taxonomy nodes staged in shared memory */
 #define NH_WARP_HASH_SLOTS 64       /* per-read taxon->count table (fast path) */
@@ -31,7 +33,8 @@ struct NhDbParams {
   uint32_t value_bits;
   uint32_t value_mask;
   int32_t k, l, w;           /* w = k - l + 1 */
-  int32_t tile_pos;          /* k-mer positions per tile = NH_TILE_LMERS - (w-1) */
+  int32_t tile_pos;          /* k-mer positions per tile (warp-per-tile kernels: NH_TILE_LMERS - (w-1)) */
+  int32_t legacy_tile_pos;   /* always NH_TILE_LMERS - (w-1): what minimizer_tile can stage */
   int32_t amb_span;          /* max(l, k-1): bases whose ambiguity voids a position */
   int32_t revcom_version;
   uint64_t seed_mask;        /* spaced_seed_mask, or the l-mer mask when it is 0 */
@@ -49,14 +52,15 @@ struct __align__(16) NhTile {
   uint32_t role;      /* who scores the tile's unit inside k_scan_probe_score, NH_ROLE_* */
 };
 
-/* roles of a tile in the fused kernel: a unit is scored in-warp when each of
- * its mates is at most one tile and both tiles sit in the same group of 32 */
-#define NH_ROLE_DEFERRED 0u /* unit goes to k_score (multi-tile or split across groups) */
-#define NH_ROLE_LEADER 1u   /* scores its unit from its own tile */
-#define NH_ROLE_LEADER2 2u  /* scores its unit from its own tile and tile + 1 */
-#define NH_ROLE_PARTNER 3u  /* second mate; the lane before scores the unit */
-#define NH_LANE_TAXA 8      /* per-lane taxon->count slots in the fused kernel */
-#define NH_OVERFLOW_REPROBE 0x80000000u /* overflow_units flag: taxa were not stored, probe again */
+/* role of a tile in the streaming kernel: a unit (read or pair) is scored inside the warp when all
+ * its tiles sit in one group of 32; its first tile LEADs, the others are MEMBERs that fold their
+ * hits into the leader's table */
+#define NH_ROLE_DEFERRED 0u /* unit goes to k_score (more than 32 tiles, or split across groups) */
+#define NH_ROLE_LEADER 1u   /* first tile of a unit scored in the warp */
+#define NH_ROLE_MEMBER 2u   /* | (tile index - index of the unit's first tile) << 8 */
+#define NH_ROLE_KIND(r) ((r) & 0xFFu)
+#define NH_ROLE_DELTA(r) ((r) >> 8)
+#define NH_LANE_TAXA 8      /* per-lane taxon->count slots in the streaming kernel */
 
 struct NhTileOut {
   uint32_t lk_off; /* first lookup of the tile in the lookup arrays */
@@ -77,7 +81,7 @@ struct __align__(8) NhTileSum {
 };
 #define NH_TILE_HAS 1u       /* the tile has at least one lookup */
 #define NH_TILE_FIRST_HIT 2u /* its first lookup hit (needed for the group count across tile borders) */
-#define NH_TILE_OVERFLOW 4u  /* more distinct taxa than the table holds: lk_min / lk_cnt were written instead */
+#define NH_TILE_OVERFLOW 4u  /* more distinct taxa than the table holds: k_score_big scans the unit again */
 
 /* Device-side counters of one batch. */
 struct NhCounters {
@@ -104,7 +108,7 @@ struct NhBatchPtrs {
   NhTileOut *tile_out;
   /* lookups */
   uint64_t *lk_min;
-  uint8_t *lk_cnt;          /* k-mer positions that take this lookup's taxon */
+  uint16_t *lk_cnt;         /* k-mer positions that take this lookup's taxon */
   uint32_t *lk_taxon;
   /* results */
   uint32_t *out_call;       /* external taxid per unit (may be null) */
@@ -114,8 +118,8 @@ struct NhBatchPtrs {
   uint32_t *dbg_hit_groups;
   uint32_t *overflow_units;
   uint32_t *deferred_units; /* null: k_score walks every unit (legacy path) */
-  int32_t emit_all_taxa;    /* fused kernel: store lk_taxon for every tile (per-read output wanted) */
-  NhTileTab *tile_tab;      /* streaming kernel: per-tile tables of deferred units (null: lookups in lk_*) */
+  int32_t emit_all_taxa;    /* streaming kernel: store lk_cnt / lk_taxon of every lookup (per-read output wanted) */
+  NhTileTab *tile_tab;      /* streaming kernel: per-tile tables of deferred units (null: legacy path, lookups in lk_*) */
   NhTileSum *tile_sum;
   NhCounters *counters;
   /* per-position debug output of the minimizer kernel (may be null) */
@@ -133,10 +137,10 @@ struct NhScoreParams {
 
 /* launchers (nh_kernels.cu); each returns the number of kernels launched */
 int nh_launch_plan(const NhDbParams &db, const NhBatchPtrs &b, cudaStream_t st);
-/* fused path: lane-serial minimizer scan -> probe -> in-warp scoring of short units */
+/* streaming path: lane-serial minimizer scan feeding the probe, in-warp scoring */
 bool nh_fused_supported(const NhDbParams &db);
-int nh_launch_fused(const NhDbParams &db, const NhBatchPtrs &b, const NhScoreParams &sp,
-                    uint32_t tiles_upper, int sm_count, int form /* 1 phased, 2 streaming */, cudaStream_t st);
+int nh_launch_stream(const NhDbParams &db, const NhBatchPtrs &b, const NhScoreParams &sp,
+                     uint32_t tiles_upper, int sm_count, cudaStream_t st);
 int nh_launch_minimizers(const NhDbParams &db, const NhBatchPtrs &b, uint32_t tiles_upper,
                          int sm_count, cudaStream_t st);
 int nh_launch_probe(const NhDbParams &db, const uint64_t *keys, uint32_t *taxa,
@@ -145,7 +149,7 @@ int nh_launch_score(const NhDbParams &db, const NhBatchPtrs &b, const NhScorePar
                     int sm_count, cudaStream_t st);
 /* per-tile runs (external taxid, k-mer count) packed densely for the per-read kraken output */
 int nh_launch_gather_runs(const NhDbParams &db, const NhBatchPtrs &b, uint32_t tiles_upper,
-                          uint32_t *run_ext, uint8_t *run_len, uint32_t *tile_run_off,
+                          uint32_t *run_ext, uint16_t *run_len, uint32_t *tile_run_off,
                           uint32_t *cursor, int sm_count, cudaStream_t st);
 int nh_launch_random_gather(const uint32_t *cells, uint64_t n_sectors, uint64_t n_reads,
                             uint64_t seed, uint32_t *sink, int sm_count, cudaStream_t st);

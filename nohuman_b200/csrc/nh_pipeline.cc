@@ -1029,7 +1029,7 @@ struct Work {
   std::vector<uint32_t> call;
   std::vector<uint8_t> keep;
   std::vector<uint32_t> first_run, run_ext; /* per-sequence hit runs (kraken output only) */
-  std::vector<uint8_t> run_len;
+  std::vector<uint16_t> run_len;
   std::string out[2];  /* kept records of this batch, serialised by the classifier thread */
   std::string klines;  /* kraken2 --output lines of this batch */
   uint64_t n_classified = 0, bases = 0;

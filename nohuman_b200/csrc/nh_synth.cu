@@ -142,7 +142,7 @@ extern "C" int nh_synth_build_db(const void *opts, size_t opts_len, const void *
   sp.max_batch_bases = chunk_max;
   sp.max_batch_seqs = 16;
   nh_session *s = nullptr;
-  rc = nh_session_create(db, &sp, &s);
+  rc = nh_session_create_ex(db, &sp, true, &s); /* the builder runs the warp-per-tile minimizer kernel */
   if (rc) {
     nh_db_close(db);
     return rc;

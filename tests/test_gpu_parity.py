@@ -118,18 +118,16 @@ def test_edge_cases(small_db, gpu_db):
         _compare_batch(small_db, sess, pseqs, True, 0.2)
 
 
-@pytest.mark.parametrize("mode", ["legacy", "lane_taxa_1", "lane_taxa_2", "tile_pos_60", "probe_lanes_2", "probe_lanes_4"])
+@pytest.mark.parametrize("mode", ["legacy", "lane_taxa_1", "lane_taxa_2", "tile_pos_60", "tile_pos_252", "tile_pos_1023"])
 def test_kernel_path_variants_match_oracle(small_db, gpu_db, mode, monkeypatch):
-    """The warp-per-tile kernels (NH_LEGACY_KERNELS=1) and the fused kernel with a
-    shrunken in-warp taxon table (units overflow into k_score_big, which probes
-    again) give the same answers as the default fused path and the oracle."""
+    """The warp-per-tile kernels (NH_LEGACY_KERNELS=1), the streaming kernel with a shrunken
+    in-warp taxon table (units overflow into k_score_big, which classifies them again from
+    their bases) and other tile sizes give the answers of the default path and of the oracle."""
     from nohuman_b200 import Session
     if mode == "legacy":
         monkeypatch.setenv("NH_LEGACY_KERNELS", "1")
     elif mode.startswith("tile_pos"):
-        monkeypatch.setenv("NH_FUSED_TILE_POS", mode.split("_")[-1])  # every 150 bp read becomes a multi-tile unit
-    elif mode.startswith("probe_lanes"):
-        pytest.skip("NH_PROBE_LANES is read once per process; covered by running the suite with it set")
+        monkeypatch.setenv("NH_FUSED_TILE_POS", mode.split("_")[-1])  # 60: every 150 bp read becomes a multi-tile unit
     else:
         monkeypatch.setenv("NH_TEST_LANE_TAXA", mode[-1])
     g = dict(small_db.genomes)
@@ -148,3 +146,64 @@ def test_kernel_path_variants_match_oracle(small_db, gpu_db, mode, monkeypatch):
         assert bool(st.fused_kernel) == (mode != "legacy" and os.environ.get("NH_LEGACY_KERNELS") != "1")
     assert st.n_classified == int((want["call"] != 0).sum())
     assert len(set(want["call"].tolist())) > 4
+
+
+@pytest.mark.parametrize("tile_pos", [508, 252, 100])
+def test_lengths_straddling_tile_and_group_borders(small_db, gpu_db, tile_pos, monkeypatch):
+    """Reads whose k-mer positions end exactly at, one before and one after a tile border, units of
+    2..33 tiles (scored in the warp when all tiles share a group of 32, by k_score otherwise), and
+    pairs whose mates fall on either side of a group border."""
+    from nohuman_b200 import Session
+    monkeypatch.setenv("NH_FUSED_TILE_POS", str(tile_pos))
+    tp = tile_pos
+    k = 35
+    g = dict(small_db.genomes)
+    src = g[9606]
+    rng = np.random.default_rng(17)
+    lens = []
+    for nt in (1, 2, 3, 5, 31, 32, 33):
+        for d in (-1, 0, 1):
+            lens.append(nt * tp + k - 1 + d)
+    lens += [k - 1, k, k + 1, tp, tp + 1, 2 * tp - 1]
+    seqs = []
+    for rep in range(3):
+        for L in lens:
+            o = int(rng.integers(0, len(src) - L - 1))
+            r = src[o:o + L].copy()
+            if rep == 1 and L > 200:
+                r[L // 2] = ord("N")  # an ambiguous stretch across a border keeps last_minimizer alive
+                r[min(L - 1, tp + k - 2)] = ord("N")
+            if rep == 2:
+                r = synth.mutate(rng, r, 0.03)
+            seqs.append(r)
+    # filler of short reads so that the long units start at many different lanes
+    short = synth.illumina_reads(small_db.genomes, 97, 150, seed=5)
+    mixed = []
+    for i, r in enumerate(seqs):
+        mixed.append(r)
+        mixed += short[(i * 3) % 90:(i * 3) % 90 + (i % 4)]
+    with Session(gpu_db, confidence=0.05) as sess:
+        _compare_batch(small_db, sess, mixed, False, 0.05)
+    pairs = mixed + mixed[1:] + [mixed[0]]  # odd shift: mates of very different lengths, units across group borders
+    if len(pairs) % 2:
+        pairs.append(short[0])
+    with Session(gpu_db, confidence=0.05, paired=True) as sess:
+        _compare_batch(small_db, sess, pairs, True, 0.05)
+
+
+def test_repeated_minimizers_across_tile_borders(small_db, gpu_db, monkeypatch):
+    """Low-complexity sequence: the same minimizer runs across tile borders, so the hit-group count
+    depends on the border repair (a tile's first lookup equals the previous tile's last one)."""
+    from nohuman_b200 import Session
+    monkeypatch.setenv("NH_FUSED_TILE_POS", "64")
+    g = dict(small_db.genomes)
+    src = g[9606]
+    seqs = []
+    for i in range(60):
+        unit = src[i * 100:i * 100 + 40 + i % 7]
+        seqs.append(np.concatenate([src[5000 + i * 10:5000 + i * 10 + 90], np.tile(unit, 12), src[9000:9100]]))
+    for i in range(20):  # homopolymers and dinucleotide repeats: one minimizer for hundreds of positions
+        seqs.append(np.concatenate([src[i * 50:i * 50 + 80], np.full(300, b"ACGT"[i % 4], np.uint8), src[700:800]]))
+        seqs.append(np.tile(np.frombuffer(b"AC", np.uint8), 250))
+    with Session(gpu_db, confidence=0.0) as sess:
+        _compare_batch(small_db, sess, seqs, False, 0.0)

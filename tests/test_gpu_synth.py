@@ -91,3 +91,106 @@ def test_synth_reads_classify_like_oracle(sdb, odb, paired, conf, ins):
     frac = (want["ext"] != 0).mean()
     assert 0.3 < frac < 0.6, frac  # ~half the units are genome-derived
     assert st.n_classified == int((want["ext"] != 0).sum()) == st2.n_classified
+
+
+@pytest.fixture(scope="module")
+def big_sdb():
+    """2^26 + 5 cells (256 MiB, far beyond L2-resident probing of a toy table), built on the GPU"""
+    from nohuman_b200 import synth
+    s = synth.build_synthetic_db(capacity=(1 << 26) + 5, device=0)
+    yield s
+    s.db.close()
+
+
+@pytest.fixture(scope="module")
+def big_odb(big_sdb, oracle):
+    import tempfile
+    d = tempfile.mkdtemp()
+    big_sdb.save(d)
+    return oracle.OracleDb.load(d)
+
+
+def _ont_lengths(rng, n, n50=10_000, lo=200, hi=100_000):
+    sigma = 0.9
+    mu = np.log(n50) - sigma * sigma  # length-weighted median of a log-normal = exp(mu + sigma^2)
+    L = np.exp(rng.normal(mu, sigma, size=n)).astype(np.int64)
+    L = np.clip(L, lo, hi)
+    L[:6] = [hi, hi - 1, 50_000, 75_001, 16_290, 16_291]  # the longest reads and a few exact tile multiples
+    return L
+
+
+def test_ont_reads_up_to_100kb_match_oracle(big_sdb, big_odb):
+    """BASELINE configs[2] shape at the scale it is quoted: log-normal lengths with N50 ~10 kb up to
+    100 kb (hundreds of tiles, many 32-tile groups, k_score merging tile tables), 5 % errors,
+    keep-human, against a GPU-built 2^26-cell table."""
+    import torch
+    from nohuman_b200 import Session, synth
+    rng = np.random.default_rng(26)
+    n = 3500
+    lens = _ont_lengths(rng, n)
+    offsets = np.zeros(n + 1, np.int64)
+    np.cumsum(lens, out=offsets[1:])
+    total = int(offsets[-1])
+    assert total > 20_000_000 and lens.max() == 100_000
+    d_off = torch.from_numpy(offsets).cuda()
+    d_bases = torch.zeros(total + 64, dtype=torch.uint8, device="cuda")
+    e = 0.05 / 3
+    synth.synth_reads(0, d_bases.data_ptr(), d_off.data_ptr(), n, big_sdb.genome_seed, big_sdb.genome_bases, seed=4,
+                      human_frac=0.5, sub_rate=e, ins_rate=e, del_rate=e, n_rate=0.02)
+    torch.cuda.synchronize()
+    bases = d_bases[:total].cpu().numpy()
+    for conf in (0.0, 0.2):
+        with Session(big_sdb.db, confidence=conf, keep_human=True, max_batch_bases=total + 1024, max_batch_seqs=n) as sess:
+            call, keep, st = sess.classify(bases, offsets.astype(np.uint64))
+            icall, tk, hg = sess.debug_last_batch(n)
+        big_odb.confidence = conf
+        want = big_odb.classify_batch(bases, offsets.astype(np.uint64), paired=False)
+        np.testing.assert_array_equal(tk, want["total_kmers"])
+        np.testing.assert_array_equal(hg, want["hit_groups"])
+        np.testing.assert_array_equal(call, want["ext"])
+        np.testing.assert_array_equal(keep, (want["ext"] != 0).astype(np.uint8))
+    assert 0.3 < (call != 0).mean() < 0.7
+
+
+def test_replica_adopted_from_device_memory(big_sdb, big_odb):
+    """Database.from_memory(cells_on_device=True): the path ranks 1..N-1 take after the NCCL broadcast —
+    the cell array is adopted in place (no copy).  The replica must answer exactly like the original."""
+    import torch
+    from nohuman_b200 import Database, Session, synth
+    from nohuman_b200 import dist as nhd
+    cap = int(big_sdb.db.info.capacity)
+    nbytes = nhd.padded_cells(cap) * 4
+    src = torch.as_tensor(_DevPtr(big_sdb.db.device_cells_ptr(), nbytes), device="cuda")
+    replica_cells = src.clone()  # what dist.broadcast_table leaves on a non-source rank
+    assert replica_cells.data_ptr() % 128 == 0
+    rep = Database.from_memory(big_sdb.opts, big_sdb.taxo, big_sdb.hash_header(), replica_cells.data_ptr(), device=0,
+                               cells_on_device=True)
+    try:
+        assert rep.device_cells_ptr() == replica_cells.data_ptr()
+        n_pairs = 20000
+        n_seqs, L = 2 * n_pairs, 150
+        d_off = torch.arange(n_seqs + 1, dtype=torch.int64, device="cuda") * L
+        d_bases = torch.zeros(n_seqs * L + 64, dtype=torch.uint8, device="cuda")
+        synth.synth_reads(0, d_bases.data_ptr(), d_off.data_ptr(), n_seqs, big_sdb.genome_seed, big_sdb.genome_bases,
+                          seed=77, paired=True, n_rate=0.01)
+        torch.cuda.synchronize()
+        bases = d_bases[:n_seqs * L].cpu().numpy()
+        offsets = d_off.cpu().numpy().astype(np.uint64)
+        with Session(rep, confidence=0.5, paired=True) as s1, Session(big_sdb.db, confidence=0.5, paired=True) as s0:
+            c1, k1, _ = s1.classify(bases, offsets)
+            c0, k0, _ = s0.classify(bases, offsets)
+        big_odb.confidence = 0.5
+        want = big_odb.classify_batch(bases, offsets, paired=True)
+        np.testing.assert_array_equal(c1, want["ext"])
+        np.testing.assert_array_equal(c0, c1)
+        np.testing.assert_array_equal(k0, k1)
+    finally:
+        rep.close()
+    # closing the replica must not free memory it does not own
+    assert int(replica_cells[:4096].sum().item()) == int(src[:4096].sum().item())
+
+
+class _DevPtr:
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3,
+                                         "strides": None}
