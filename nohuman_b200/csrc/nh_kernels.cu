@@ -747,9 +747,13 @@ k_score_big(const NhDbParams db, const NhBatchPtrs b, const NhScoreParams sp) {
  * default k=35, l=31 gives W=5); other databases take the warp-per-tile kernels.
  */
 
+#ifndef NH_BCHUNK_WORDS
 #define NH_BCHUNK_WORDS 8u                            /* base words (4 bases each) per lane and chunk */
+#endif
 #define NH_BCHUNK_STRIDE (NH_BCHUNK_WORDS * 4u + 16u) /* + up to 12 bytes of 16-byte misalignment */
+#ifndef NH_PQ_SLOTS
 #define NH_PQ_SLOTS 128u
+#endif
 #define NH_META_FIRST 0x8000u /* the first lookup of its tile */
 #define NH_AUX_NONE 0xFFFFFFFFu
 
@@ -775,6 +779,16 @@ struct __align__(16) StreamWarpSmem {
   uint32_t pq_slot[EMIT ? NH_PQ_SLOTS : 1]; /* per-read output only: where the lookup's taxon goes */
   uint32_t q_slot[EMIT ? 32 : 1];
 };
+
+/* 3 blocks of 8 warps per SM (up to 85 registers): the overlap of table latency and scan happens
+ * inside the warp, so registers are worth more than resident warps */
+#ifndef NH_STREAM_MIN_BLOCKS
+#define NH_STREAM_MIN_BLOCKS 3
+#endif
+/* NH_STREAM_MIN_BLOCKS blocks of NH_WARPS_PER_BLOCK warps must fit the SM's 227 KB next to the staged
+ * parent array of a small taxonomy and the 1 KB the system reserves per block */
+static_assert((sizeof(StreamWarpSmem<false>) * NH_WARPS_PER_BLOCK + 1024 + 512) * NH_STREAM_MIN_BLOCKS <= 227 * 1024,
+              "k_stream_classify would no longer fit its blocks per SM");
 
 template <typename SM>
 __device__ __forceinline__ uint32_t lane_tab_get(const SM &sm, uint32_t lane, uint32_t n, uint32_t taxon) {
@@ -818,11 +832,6 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
   return v;
 }
 
-/* 3 blocks of 8 warps per SM (up to 85 registers): the overlap of table latency and scan happens
- * inside the warp, so registers are worth more than resident warps */
-#ifndef NH_STREAM_MIN_BLOCKS
-#define NH_STREAM_MIN_BLOCKS 3
-#endif
 #ifndef NH_STREAM_CHECK_MASK
 #define NH_STREAM_CHECK_MASK 1 /* probe check after bases with (j & mask) == mask: 1 -> every 2nd base */
 #endif
@@ -831,6 +840,8 @@ template <int W, bool DBG, bool REV0, bool EMIT>
 __global__ void __launch_bounds__(NH_BLOCK_THREADS, NH_STREAM_MIN_BLOCKS)
 k_stream_classify(const NhDbParams db, const NhBatchPtrs b, const NhScoreParams sp) {
   static_assert(W == 5, "the scan consumes one 4-byte word per ring rotation");
+  static_assert(NH_PQ_SLOTS >= 31u + 32u * (NH_STREAM_CHECK_MASK + 1u), "runs closed between two probe checks must fit the ring");
+  static_assert((NH_PQ_SLOTS & (NH_PQ_SLOTS - 1u)) == 0 && (NH_BCHUNK_WORDS & (NH_BCHUNK_WORDS - 1u)) == 0, "powers of two");
   typedef StreamWarpSmem<EMIT> Smem;
   extern __shared__ __align__(16) uint32_t s_dyn[];
   uint32_t *s_parent = s_dyn;
@@ -1113,7 +1124,7 @@ k_stream_classify(const NhDbParams db, const NhBatchPtrs b, const NhScoreParams 
           cnt = newrun ? 1u : cnt + (nonamb ? 1u : 0u);
           last = newrun ? mz : last;
           if ((j & NH_STREAM_CHECK_MASK) == NH_STREAM_CHECK_MASK) {
-            while (pq_n + cq_n >= 32u) probe_round();
+            while (pq_n >= 32u) probe_round(); /* cq_n is 0 between rounds */
           }
         }
       };

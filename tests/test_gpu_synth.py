@@ -149,7 +149,10 @@ def test_ont_reads_up_to_100kb_match_oracle(big_sdb, big_odb):
         np.testing.assert_array_equal(hg, want["hit_groups"])
         np.testing.assert_array_equal(call, want["ext"])
         np.testing.assert_array_equal(keep, (want["ext"] != 0).astype(np.uint8))
-    assert 0.3 < (call != 0).mean() < 0.7
+        frac = float((call != 0).mean())
+        # half the reads come from the genome; with 5 % errors only 0.95^35 = 17 % of their k-mers survive,
+        # so --conf 0.2 calls few of them while --conf 0 calls nearly all
+        assert (0.4 < frac < 0.6) if conf == 0.0 else (0.02 < frac < 0.4), (conf, frac)
 
 
 def test_replica_adopted_from_device_memory(big_sdb, big_odb):
