@@ -3,20 +3,31 @@
 + keep/drop) on B200.
 
     python bench.py --gpus N --steps K --warmup W            # this repo (CUDA)
-    python bench.py --impl reference --gpus N ...            # CPU baseline arm
+    python bench.py --impl reference --gpus N ...            # CPU arm (no CUDA library loaded)
 
-A step is one pass of the four kernels (plan -> minimizers -> hash probe ->
-score/decide) over one batch of synthetic reads of BASELINE.json configs[1]'s
-shape: 2x150 bp paired-end Illumina reads, 50 % sampled from the genome the
-database was built from ("human-derived"), --conf 0.5, against a synthetic
-kraken2-format table sized like HPRC.r2 (default 2^31 cells = 8 GiB, load 0.7).
-`value` is measured with the batch already resident in HBM; `e2e` goes through
-nh_classify_batch with HOST buffers (H2D + D2H inside the timed region).
+Workload = BASELINE.json configs[1]: 10 M synthetic 2x150 bp read pairs, 50 %
+sampled from the genome the table was built from ("human-derived"), --conf 0.5,
+against a synthetic kraken2-format table sized like HPRC.r2 (configs[3]:
+2^31 cells = 8 GiB, load 0.7).  One step = those 10 M pairs per GPU = ten
+launches of 1 M pairs over ten different batches.  `value` is measured with
+the batches resident in HBM; `e2e` goes through nh_classify_batch with pinned
+HOST buffers (H2D + D2H inside the timed region).
 
-The reference arm times the CPU implementation of the same path (the oracle
-port of kraken2's classifier; the real kraken2 binary is unavailable offline)
-on the GPU box's host cores.  oracle/ is imported ONLY in cpu_baseline() and
-the reference arm.
+Outside the headline timing the line also carries
+  parity_vs_oracle   every rank classifies one common batch on ITS replica of the
+                     table; mismatches against the CPU oracle are summed over ranks
+  workloads          configs[2] (ONT-like long reads, keep-human) and configs[4]
+                     (read-length sweep 100 bp - 50 kb), each with Gbp/s, lookups/s,
+                     fraction of the measured table-request ceiling and an oracle
+                     parity sample of >= 20 Mbp, at whatever N the run has
+  roofline_probe     the probe's own access pattern measured alone on the same table
+
+The reference arm times the CPU implementation of the same path — the oracle's
+restatement of kraken2's classifier (kraken2 itself is not installable offline)
+— on the host cores.  It builds the same table and samples the same reads with
+the CPU twin of the generator (oracle/k2_synth.c) and never imports torch or
+loads libnohuman_gpu.so.  oracle/ is touched ONLY in cpu_baseline(), the parity
+checks and the reference arm.
 """
 from __future__ import annotations
 
@@ -37,6 +48,8 @@ READ_LEN = 150
 CONF = 0.5
 METRIC = "classified+filtered throughput (Gbp/s)"
 UNIT = "Gbp/s"
+GENOME_SEED = 0x5EED
+COMMON_SEED = 424242  # the batch every rank classifies for the parity check
 
 
 def parse_args():
@@ -46,12 +59,38 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--capacity-log2", type=int, default=31, help="hash table cells = 2^this")
-    ap.add_argument("--pairs-per-step", type=int, default=1_000_000, help="read pairs per GPU per step")
+    ap.add_argument("--pairs-per-launch", type=int, default=1_000_000, help="read pairs per kernel launch")
+    ap.add_argument("--launches-per-step", type=int, default=10, help="launches (different batches) per step and GPU")
     ap.add_argument("--ref-pairs-per-step", type=int, default=0,
-                    help="reference arm: pairs per step (0 = sized for ~3 s per step)")
+                    help="reference arm: pairs per step (0 = sized for ~1 s per step)")
+    ap.add_argument("--workload-mbases", type=int, default=150, help="bases per GPU of each `workloads` entry")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-workloads", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
     return ap.parse_args()
+
+
+def workload_config(args):
+    """What is measured; identical in both arms."""
+    capacity = 1 << args.capacity_log2
+    return {
+        "workload": "BASELINE configs[1]: 10M 2x150 bp paired-end reads per step, 50% genome-derived, --conf 0.5, "
+                    "against configs[3]'s synthetic HPRC.r2-sized kraken2 table",
+        "pairs_per_step_per_gpu": args.pairs_per_launch * args.launches_per_step,
+        "pairs_per_launch": args.pairs_per_launch, "launches_per_step": args.launches_per_step,
+        "read_len": READ_LEN, "confidence": CONF, "table_cells": capacity,
+        "table_gib": round(capacity * 4 / 2 ** 30, 2), "table_target_load": 0.7, "k": 35, "l": 31,
+        "read_sampler": "50% from the table's synthetic genome (first 2*table_cells bases), 0.5% substitutions, "
+                        "1% of reads with an N, insert 350+-50; same bytes on GPU and CPU generators",
+        "l2_policy": "inputs larger than L2: ten different 300 MB batches per step + random probes over the 8 GiB table",
+    }
+
+
+def read_span(capacity):
+    """Reads are sampled from this prefix of the synthetic genome: known to both arms without building
+    the table (a table at load 0.7 always covers more than 2 bases per cell)."""
+    return 2 * capacity
 
 
 def peaks():
@@ -65,9 +104,7 @@ def peaks():
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed regions.  The
     sampler runs from before warm-up to the end of the bench; `mark()` brackets
-    the timed regions and only samples whose timestamp falls inside one count
-    (if a region is shorter than the sampling period, the samples taken under
-    the same load just before it are used and `window` says so)."""
+    the timed regions and only samples whose timestamp falls inside one count."""
 
     FIELDS = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -79,15 +116,12 @@ class ClockSampler:
         self.proc = None
         self.lines = []
         self.windows = []
-        self.t_first = None
 
     def start(self):
-        import datetime
-        self.t_first = datetime.datetime.now()
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
-                 "--format=csv,noheader,nounits", "-lms", "50"],
+                 "--format=csv,noheader,nounits", "-lms", "25"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -99,7 +133,6 @@ class ClockSampler:
             self.lines.append(line.strip())
 
     def mark(self):
-        """returns a token; call close(token) at the end of the region"""
         import datetime
         self.windows.append([datetime.datetime.now(), None])
         return len(self.windows) - 1
@@ -112,7 +145,7 @@ class ClockSampler:
         import datetime
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi not sampled on this rank"]}
-        time.sleep(0.12)
+        time.sleep(0.1)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
@@ -129,13 +162,6 @@ class ClockSampler:
             except ValueError:
                 continue
         inside = [r for r in rows if any(w0 <= r[0] <= (w1 or r[0]) for w0, w1 in self.windows)]
-        window = "timed regions"
-        if not inside and self.windows:
-            # regions shorter than the sampling period: the warm-up just before runs the same kernels
-            w0 = self.windows[0][0] - datetime.timedelta(seconds=1.0)
-            w1 = max(w[1] or w[0] for w in self.windows) + datetime.timedelta(seconds=0.1)
-            inside = [r for r in rows if w0 <= r[0] <= w1]
-            window = "timed regions + 1 s of warm-up before them"
         reasons = set()
         for r in inside:
             for nm, v in zip(self.NAMES, r[4]):
@@ -146,7 +172,7 @@ class ClockSampler:
                 "sm_max_mhz": inside[0][2] if inside else (rows[0][2] if rows else None),
                 "power_w_max": max((r[3] for r in inside), default=None),
                 "reasons": sorted(reasons), "samples": len(sm), "samples_total": len(rows),
-                "window": window}
+                "window": "timed regions (device-resident steps and e2e steps)"}
 
 
 class DevPtr:
@@ -157,22 +183,61 @@ class DevPtr:
                                          "version": 3, "strides": None}
 
 
-def make_batch(torch, synth, device, sdb_meta, n_pairs, seed):
-    n_seqs = 2 * n_pairs
-    total = n_seqs * READ_LEN
-    d_off = (torch.arange(n_seqs + 1, dtype=torch.int64, device="cuda") * READ_LEN)
-    d_bases = torch.zeros(total + 64, dtype=torch.uint8, device="cuda")
-    synth.synth_reads(device, d_bases.data_ptr(), d_off.data_ptr(), n_seqs, sdb_meta["genome_seed"],
-                      sdb_meta["genome_bases"], seed=seed, human_frac=0.5, sub_rate=0.005,
-                      n_rate=0.01, paired=True, insert_mean=350.0, insert_sd=50.0,
-                      stream=torch.cuda.current_stream().cuda_stream)
-    torch.cuda.synchronize()
-    return d_bases, d_off, n_seqs, total
+# ---------------------------------------------------------------------------------------------
+# workload shapes (shared by the GPU generator and its CPU twin)
+
+def pair_offsets(n_pairs):
+    return (np.arange(2 * n_pairs + 1, dtype=np.int64) * READ_LEN)
 
 
-def cpu_baseline(cells, sdb_meta, opts_b, taxo_b, hdr, bases, offsets, target_s=12.0, threads=0):
-    """The oracle port of kraken2's classifier on the host cores (bounded sample)."""
-    from oracle import k2oracle  # the only place bench.py touches oracle/
+READS_PE = dict(human_frac=0.5, sub_rate=0.005, ins_rate=0.0, del_rate=0.0, n_rate=0.01, paired=True,
+                insert_mean=350.0, insert_sd=50.0)
+
+
+def ont_lengths(rng, total_bases, n50=10_000, lo=200, hi=100_000):
+    """log-normal read lengths whose length-weighted median (N50) is ~10 kb, clipped to [200, 100k]"""
+    sigma = 0.9
+    mu = np.log(n50) - sigma * sigma
+    out = []
+    acc = 0
+    while acc < total_bases:
+        L = np.clip(np.exp(rng.normal(mu, sigma, size=4096)).astype(np.int64), lo, hi)
+        out.append(L)
+        acc += int(L.sum())
+    L = np.concatenate(out)
+    n = int(np.searchsorted(np.cumsum(L), total_bases)) + 1
+    L = L[:n]
+    L[0] = hi  # the longest read the config allows is always present
+    return L
+
+
+def workload_list(args):
+    """BASELINE configs[2] and configs[4].  (name, lengths or read length, sampler arguments, conf, keep_human, paired)"""
+    e = 0.05 / 3
+    ont = dict(human_frac=0.5, sub_rate=e, ins_rate=e, del_rate=e, n_rate=0.01, paired=False)
+    ill = dict(human_frac=0.5, sub_rate=0.005, ins_rate=0.0, del_rate=0.0, n_rate=0.01, paired=False)
+    w = [("configs[2] ONT N50~10kb <=100kb 5% error keep-human", "ont", ont, 0.0, True, False)]
+    for L in (100, 250, 300, 500, 1000, 10_000, 50_000):
+        w.append((f"configs[4] sweep {L} bp single-end", L, ont if L >= 1000 else ill, 0.0, True, False))
+    return w
+
+
+def workload_offsets(shape, total_bases, seed):
+    if shape == "ont":
+        L = ont_lengths(np.random.default_rng(seed), total_bases)
+    else:
+        n = max(64, total_bases // int(shape))
+        L = np.full(n, int(shape), np.int64)
+    off = np.zeros(len(L) + 1, np.int64)
+    np.cumsum(L, out=off[1:])
+    return off
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU side (oracle): the only functions that touch oracle/
+
+def oracle_db_from_cells(cells, opts_b, taxo_b, hdr):
+    from oracle import k2oracle
     import ctypes as C
     import tempfile
     d = tempfile.mkdtemp(prefix="nh_bench_db_")
@@ -184,9 +249,11 @@ def cpu_baseline(cells, sdb_meta, opts_b, taxo_b, hdr, bases, offsets, target_s=
     opts, tax = k2oracle.IndexOptions(), k2oracle.Taxonomy()
     assert L.k2o_load_opts(os.path.join(d, "opts.k2d").encode(), C.byref(opts)) == 0
     assert L.k2o_load_taxonomy(os.path.join(d, "taxo.k2d").encode(), C.byref(tax)) == 0
-    odb = k2oracle.OracleDb.from_arrays(opts, tax, cells, hdr[0], hdr[1], hdr[3])
-    odb.confidence = CONF
-    cores = threads or os.cpu_count() or 1
+    return k2oracle.OracleDb.from_arrays(opts, tax, cells, hdr[0], hdr[1], hdr[3])
+
+
+def cpu_timed_sample(odb, bases, offsets, target_s, cores):
+    """Oracle classification of a bounded prefix of (bases, offsets): ~target_s seconds of CPU work."""
     n_pairs_all = (len(offsets) - 1) // 2
 
     def run(n_pairs):
@@ -201,273 +268,352 @@ def cpu_baseline(cells, sdb_meta, opts_b, taxo_b, hdr, bases, offsets, target_s=
     n = int(min(n_pairs_all, max(probe_n, rate * target_s)))
     t, r = run(n)
     passes = 1
-    if n == n_pairs_all and t < 0.6 * target_s:
-        # the whole batch is faster than the sample budget: repeat it
+    if n == n_pairs_all and t < 0.6 * target_s:  # the whole batch is faster than the budget: repeat it
         extra = int(min(30, max(1, round(target_s / max(t, 1e-3)) - 1)))
         for _ in range(extra):
             t += run(n)[0]
         passes += extra
-    return odb, {"pairs": n, "passes": passes, "seconds": t, "gbp_s": passes * n * 2 * READ_LEN / t / 1e9,
-                 "reads_s": passes * 2 * n / t, "cores": cores, "result": r}
+    return {"pairs": n, "passes": passes, "seconds": t, "gbp_s": passes * n * 2 * READ_LEN / t / 1e9,
+            "reads_s": passes * 2 * n / t, "cores": cores, "result": r}
 
+
+# ---------------------------------------------------------------------------------------------
 
 def main():
     args = parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if args.impl == "reference" and rank != 0:
-        return 0
+    if args.impl == "reference":
+        return 0 if rank != 0 else reference_arm(args)
 
     import torch
     import torch.distributed as dist
     from nohuman_b200 import Database, Session, synth
+    from nohuman_b200 import dist as nhd
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback exists)")
     torch.cuda.set_device(local_rank)
     dev = local_rank
-    use_dist = world > 1 and args.impl == "ours"
+    use_dist = world > 1
     if use_dist:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-
-    # ---------------- database: built on rank 0, replicated over NCCL/NVLink ----------------
-    from nohuman_b200 import dist as nhd
-    capacity = 1 << args.capacity_log2
-    t_build0 = time.perf_counter()
-    sdb = None
-    cells = hdr = opts_b = taxo_b = None
-    gmeta = torch.zeros(1, dtype=torch.int64, device="cuda")
-    if rank == 0:
-        sdb = synth.build_synthetic_db(capacity, device=dev)
-        opts_b, taxo_b = sdb.opts, sdb.taxo
-        hdr = sdb.hash_header()
-        gmeta[0] = sdb.genome_bases
-        db = sdb.db
-    keep_alive = None
-    if use_dist:
-        dist.broadcast(gmeta, 0)
-        if rank == 0:
-            cells = torch.as_tensor(DevPtr(sdb.db.device_cells_ptr(), nhd.padded_cells(capacity) * 4), device="cuda")
-        cells, hdr, opts_b, taxo_b = nhd.broadcast_table(cells, hdr, opts_b, taxo_b, torch.device("cuda", dev))
-        torch.cuda.synchronize()
-        if rank != 0:
-            keep_alive = cells
-            db = Database.from_memory(opts_b, taxo_b, hdr, cells.data_ptr(), device=dev, cells_on_device=True)
-    sdb_meta = {"genome_seed": 0x5EED, "genome_bases": int(gmeta.item())}
-    t_build = time.perf_counter() - t_build0
-
-    n_pairs = args.pairs_per_step
-    n_bufs = 2
-    bufs = [make_batch(torch, synth, dev, sdb_meta, n_pairs, seed=1000 * (rank + 1) + b)
-            for b in range(n_bufs)]
-    n_seqs, total = bufs[0][2], bufs[0][3]
-
-    if args.impl == "reference":
-        return reference_arm(args, torch, sdb, sdb_meta, opts_b, taxo_b, hdr, bufs)
-
-    # ---------------- device-resident timing (`value`) ----------------
-    sess = Session(db, confidence=CONF, paired=True, max_batch_bases=total + 4096,
-                   max_batch_seqs=n_seqs)
-    d_call = torch.empty(n_pairs, dtype=torch.int32, device="cuda")
-    d_keep = torch.empty(n_pairs, dtype=torch.uint8, device="cuda")
-    ext = torch.cuda.ExternalStream(sess.stream)
-
-    def step(i):
-        b = bufs[i % n_bufs]
-        sess.classify_device(b[0].data_ptr(), b[1].data_ptr(), n_seqs, total, d_call.data_ptr(),
-                             d_keep.data_ptr())
-        return sess.sync()
-
-    sampler = ClockSampler(dev)
-    if rank == 0:  # one nvidia-smi poller per run is enough; rank 0's GPU is the one reported
-        sampler.start()
-    for i in range(args.warmup):
-        st = step(i)
-    random_gbs = db.random_gather_gbs(1 << 27, 3) if rank == 0 else None
 
     def barrier():
         if use_dist:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(x):
+        if not use_dist:
+            return float(x)
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if not use_dist:
+            return int(x)
+        t = torch.tensor([int(x)], dtype=torch.int64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return int(t.item())
+
+    # ---------------- database: built on rank 0, replicated over NCCL/NVLink ----------------
+    capacity = 1 << args.capacity_log2
+    span = read_span(capacity)
+    t_build0 = time.perf_counter()
+    sdb = None
+    cells = hdr = opts_b = taxo_b = None
+    if rank == 0:
+        sdb = synth.build_synthetic_db(capacity, device=dev, genome_seed=GENOME_SEED)
+        assert sdb.genome_bases >= span, (sdb.genome_bases, span)
+        opts_b, taxo_b = sdb.opts, sdb.taxo
+        hdr = sdb.hash_header()
+        db = sdb.db
+    t_build = time.perf_counter() - t_build0
+    keep_alive = None
+    t_bcast = 0.0
+    if use_dist:
+        t0 = time.perf_counter()
+        if rank == 0:
+            cells = torch.as_tensor(DevPtr(sdb.db.device_cells_ptr(), nhd.padded_cells(capacity) * 4), device="cuda")
+        cells, hdr, opts_b, taxo_b = nhd.broadcast_table(cells, hdr, opts_b, taxo_b, torch.device("cuda", dev))
+        torch.cuda.synchronize()
+        t_bcast = time.perf_counter() - t0
+        if rank != 0:
+            keep_alive = cells
+            db = Database.from_memory(opts_b, taxo_b, hdr, cells.data_ptr(), device=dev, cells_on_device=True)
+    # every replica must hold the bytes rank 0 built: 64-bit word sum of the cell array, compared on all ranks
+    dcells = torch.as_tensor(DevPtr(db.device_cells_ptr(), capacity * 4), device="cuda")
+    checksum = int(dcells.view(torch.int64).sum().item())
+    replicas_equal = True
+    if use_dist:
+        sums = [None] * world
+        dist.all_gather_object(sums, checksum)
+        replicas_equal = all(s == sums[0] for s in sums)
+    del dcells
+
+    n_pairs = args.pairs_per_launch
+    n_seqs = 2 * n_pairs
+    total = n_seqs * READ_LEN
+    d_off = torch.from_numpy(pair_offsets(n_pairs)).cuda()
+
+    def make_pe_batch(seed):
+        d_bases = torch.zeros(total + 64, dtype=torch.uint8, device="cuda")
+        synth.synth_reads(dev, d_bases.data_ptr(), d_off.data_ptr(), n_seqs, GENOME_SEED, span, seed=seed,
+                          stream=torch.cuda.current_stream().cuda_stream, **READS_PE)
+        return d_bases
+
+    n_launch = args.launches_per_step
+    bufs = [make_pe_batch(1000 * (rank + 1) + b) for b in range(n_launch)]
+    torch.cuda.synchronize()
+
+    # ---------------- device-resident timing (`value`) ----------------
+    sess = Session(db, confidence=CONF, paired=True, max_batch_bases=total + 4096, max_batch_seqs=n_seqs)
+    d_call = torch.empty(n_pairs, dtype=torch.int32, device="cuda")
+    d_keep = torch.empty(n_pairs, dtype=torch.uint8, device="cuda")
+    ext = torch.cuda.ExternalStream(sess.stream)
+
+    def launch(i):
+        sess.classify_device(bufs[i % n_launch].data_ptr(), d_off.data_ptr(), n_seqs, total, d_call.data_ptr(),
+                             d_keep.data_ptr())
+        return sess.sync()
+
+    sampler = ClockSampler(dev)
+    if rank == 0:  # one nvidia-smi poller per run is enough; rank 0's GPU is the one reported
+        sampler.start()
+    for i in range(args.warmup * n_launch):
+        st = launch(i)
+
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    stage = {"plan": 0.0, "minimizer": 0.0, "probe": 0.0, "score": 0.0}
-    lookups = tiles = launches = classified = 0
-    fused = False
+    stage = {"plan": 0.0, "stream_classify": 0.0, "probe": 0.0, "score_deferred": 0.0}
+    lookups = sectors = launches = classified = 0
     fused_form = 0
     barrier()
     tok = sampler.mark()
     torch.cuda.cudart().cudaProfilerStart()  # `ncu --profile-from-start off` sees the timed steps only
     ev0.record(ext)
-    for i in range(args.steps):
-        st = step(i)
+    for i in range(args.steps * n_launch):
+        st = launch(i)
         stage["plan"] += st.ms_plan
-        stage["minimizer"] += st.ms_minimizer
+        stage["stream_classify"] += st.ms_minimizer
         stage["probe"] += st.ms_probe
-        stage["score"] += st.ms_score
+        stage["score_deferred"] += st.ms_score
         lookups += st.n_lookups
-        tiles += st.n_tiles
+        sectors += st.n_sector_reads
         launches += st.gpu_launches
         classified += st.n_classified
-        fused = bool(st.fused_kernel)
         fused_form = int(st.fused_kernel)
     ev1.record(ext)
     barrier()
     torch.cuda.cudart().cudaProfilerStop()
     sampler.close(tok)
-    ms_total = ev0.elapsed_time(ev1)
-    if use_dist:
-        t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
+    ms_total = max_over_ranks(ev0.elapsed_time(ev1))
     ms_step = ms_total / args.steps
-    gbp_s = world * n_pairs * 2 * READ_LEN * args.steps / (ms_total * 1e-3) / 1e9
-    reads_s = world * n_seqs * args.steps / (ms_total * 1e-3)
+    n_timed = args.steps * n_launch
+    gbp_s = world * n_pairs * 2 * READ_LEN * n_timed / (ms_total * 1e-3) / 1e9
+    reads_s = world * n_seqs * n_timed / (ms_total * 1e-3)
+    if fused_form != 2:  # warp-per-tile kernels (NH_LEGACY_KERNELS=1): the stages are separate kernels
+        stage = {"plan": stage["plan"], "minimizer": stage["stream_classify"], "probe": stage["probe"],
+                 "score": stage["score_deferred"]}
+    else:
+        del stage["probe"]
+    for kname in stage:
+        stage[kname] /= n_timed
+    lk_per_launch = lookups / n_timed
+    sec_per_launch = sectors / n_timed
 
     # ---------------- e2e through the C ABI with host buffers ----------------
     e2e = None
     if not args.no_e2e:
-        e2e = run_e2e(args, torch, dist if use_dist else None, db, bufs, n_pairs, n_seqs, total, world,
-                      sampler)
+        e2e = run_e2e(args, torch, dist if use_dist else None, db, bufs, d_off, n_pairs, n_seqs, total, world, sampler)
     clocks = sampler.stop()
+
+    # ---------------- the probe's access pattern alone: the ceiling the kernel is held to ----------------
+    probe_kernel = "stream_classify" if fused_form == 2 else "probe"
+    ms_probe_kernel = stage[probe_kernel]
+    roofline_probe = None
+    if rank == 0:
+        spill = sec_per_launch / lk_per_launch - 1.0 if sectors and lk_per_launch else 0.41
+        variants = []
+        for name, lanes, p, win in (("independent random sectors", 1, 0.0, 0),
+                                    ("probe chains: adjacent sector after the first arrived, p = table's spill rate", 1, spill, 0),
+                                    ("2 lanes per lookup (64-byte block), p = 0.24", 2, 0.24, 0),
+                                    ("4 lanes per lookup (128-byte line), p = 0.12", 4, 0.12, 0),
+                                    ("probe chains, every SM confined to its own 64 MiB window (not reachable by a hash table)",
+                                     1, spill, 64 << 20)):
+            items_s, req_s = db.probe_pattern(lanes=lanes, p_continue=p, sm_window_bytes=win, items_per_chain=128, iters=3)
+            variants.append({"pattern": name, "lanes": lanes, "p_continue": round(p, 4), "sm_window_bytes": win,
+                             "lookups_per_s": round(items_s, 1), "requests_per_s": round(req_s, 1)})
+        reachable = [v for v in variants if v["sm_window_bytes"] == 0]
+        peak_req = max(v["requests_per_s"] for v in reachable)
+        peak_lk = max(v["lookups_per_s"] for v in reachable if v["p_continue"] > 0)
+        k_lk = lk_per_launch / (ms_probe_kernel * 1e-3)
+        k_req = (sec_per_launch if sectors else lk_per_launch) / (ms_probe_kernel * 1e-3)
+        roofline_probe = {
+            "kernel": "k_" + probe_kernel, "lookups_per_s": round(k_lk, 1), "table_requests_per_s": round(k_req, 1),
+            "sectors_per_lookup": round(sec_per_launch / lk_per_launch, 4) if sectors else None,
+            "achieved_sector_gbs": round(k_lk * 32.0 / 1e9, 1),
+            "peak_requests_per_s": peak_req, "peak_lookups_per_s": peak_lk,
+            "random_sector_peak_gbs": round(peak_req * 32.0 / 1e9, 1),
+            "frac_by_requests": round(k_req / peak_req, 4), "frac_by_lookups": round(k_lk / peak_lk, 4),
+            "frac_of_random_sector_peak": round(k_lk / peak_lk, 4),
+            "patterns": variants,
+            "note": "ceiling = the probe's own access pattern (random sector, adjacent sector one round later with the "
+                    "table's spill rate) run alone on the same table in the same process; peak_requests = best request rate "
+                    "of any pattern a hash table can produce, peak_lookups = best lookup rate among the chain patterns",
+        }
+
+    # ---------------- parity: every rank, its own replica, one common batch ----------------
+    odb = None
+    host_cells = None
+    parity = None
+    if not args.no_parity:
+        common = make_pe_batch(COMMON_SEED)
+        torch.cuda.synchronize()
+        want = torch.zeros(n_pairs, dtype=torch.int32, device="cuda")
+        n_check = n_pairs
+        if rank == 0:
+            host_cells = sdb.download_cells()
+            odb = oracle_db_from_cells(host_cells, opts_b, taxo_b, hdr)
+            odb.confidence = CONF
+            h_bases = common[:total].cpu().numpy()
+            r = odb.classify_batch(h_bases, pair_offsets(n_pairs).astype(np.uint64), paired=True)
+            want.copy_(torch.from_numpy(r["ext"].astype(np.int32)))
+        if use_dist:
+            dist.broadcast(want, 0)
+        sess.classify_device(common.data_ptr(), d_off.data_ptr(), n_seqs, total, d_call.data_ptr(), d_keep.data_ptr())
+        sess.sync()
+        mism = int((d_call != want).sum().item())
+        keep_bad = int((d_keep != (want == 0).to(torch.uint8)).sum().item())
+        parity = {"ranks_checked": sum_over_ranks(1), "pairs_checked_per_rank": n_check,
+                  "mismatches": sum_over_ranks(mism), "keep_mask_mismatches": sum_over_ranks(keep_bad),
+                  "replica_checksums_equal": bool(replicas_equal),
+                  "how": "each rank classifies the same seeded 1M-pair batch against its own replica; expected calls from "
+                         "the CPU oracle on rank 0, broadcast; counts summed over ranks"}
+        del common
+    sess.close()
+    del bufs
+    torch.cuda.empty_cache()
+
+    # ---------------- BASELINE configs[2] and configs[4], at this N ----------------
+    workloads = None
+    if not args.no_workloads:
+        peak_lk = roofline_probe["peak_lookups_per_s"] if roofline_probe else None
+        if use_dist:
+            t = torch.tensor([peak_lk or 0.0], dtype=torch.float64, device="cuda")
+            dist.broadcast(t, 0)
+            peak_lk = float(t.item()) or None
+        workloads = run_workloads(args, torch, dist if use_dist else None, db, synth, Session, odb, span, rank, world,
+                                  dev, peak_lk, max_over_ranks, sum_over_ranks)
 
     if rank != 0:
         if use_dist:
+            dist.barrier()
             dist.destroy_process_group()
         return 0
 
-    # ---------------- roofline of the dominant kernel + probe ----------------
+    # ---------------- roofline of the dominant kernel ----------------
     peak, peak_src = peaks()
-    for kname in stage:
-        stage[kname] /= args.steps
-    lk_per_step = lookups / args.steps
-    staging = lk_per_step * 13.0  # 8 B key + 1 B run length + 4 B taxon per lookup (L2-resident scratch)
-    if fused:
+    if fused_form == 2:
         # one kernel: 1 B/base read + one 32 B sector per lookup + 5 B/unit of results
-        fname = "stream_classify" if fused_form == 2 else "scan_probe_score"
-        stage = {"plan": stage["plan"], fname: stage["minimizer"], "score_deferred": stage["score"]}
-        alg = {fname: total * 1.0 + lk_per_step * 32.0 + n_pairs * 5.0, "score_deferred": 0.0, "plan": n_seqs * 8.0}
+        alg = {"stream_classify": total * 1.0 + lk_per_launch * 32.0 + n_pairs * 5.0, "score_deferred": 0.0, "plan": n_seqs * 8.0}
     else:
-        alg = {
-            # minimizer: 1 B/base read + 9 B per lookup written (8 B key + 1 B k-mer count) + 8 B/tile
-            "minimizer": total * 1.0 + lk_per_step * 9.0 + (tiles / args.steps) * 16.0,
-            # probe: one 32 B sector per lookup
-            "probe": lk_per_step * 32.0,
-            "score": lk_per_step * 5.0 + n_pairs * 5.0,
-            "plan": n_seqs * 8.0,
-        }
+        alg = {"minimizer": total * 1.0 + lk_per_launch * 10.0, "probe": lk_per_launch * 32.0,
+               "score": lk_per_launch * 6.0 + n_pairs * 5.0, "plan": n_seqs * 8.0}
     dom = max(stage, key=lambda k_: stage[k_])
-    probe_name = ("stream_classify" if fused_form == 2 else "scan_probe_score") if fused else "probe"
-
     traffic_tab = {}
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         with open(tpath) as f:
             tj = json.load(f)
         w = tj.get("workload", {})
-        if (w.get("pairs_per_step_per_gpu") == n_pairs and w.get("table_cells") == capacity
-                and w.get("read_len") == READ_LEN):
+        if w.get("pairs_per_launch") == n_pairs and w.get("table_cells") == capacity and w.get("read_len") == READ_LEN:
             traffic_tab = tj
+    ach = alg[dom] / (stage[dom] * 1e-3) / 1e9 if stage[dom] > 0 else 0.0
+    roofline = {"kernel": "k_" + dom, "bound": "hbm", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
+                "frac": round(ach / peak, 4), "traffic": traffic_tab.get("k_" + dom, {}).get("dram_bytes_per_launch"),
+                "peak_source": peak_src, "ms_per_launch": round(stage[dom], 4),
+                "algorithmic_bytes_per_launch": int(alg[dom]),
+                "note": "per launch of 1M pairs; the HBM streaming peak is the denominator the contract asks for, "
+                        "roofline_probe holds the request-rate ceiling that actually binds"}
 
-    def roof(kname):
-        ach = alg[kname] / (stage[kname] * 1e-3) / 1e9 if stage[kname] > 0 else 0.0
-        tr = traffic_tab.get("k_" + kname, {}).get("dram_bytes_per_launch")
-        return {"kernel": "k_" + kname, "bound": "hbm", "achieved": round(ach, 1), "peak": peak,
-                "unit": "GB/s", "frac": round(ach / peak, 4), "traffic": tr, "peak_source": peak_src,
-                "ms_per_launch": round(stage[kname], 4),
-                "algorithmic_bytes_per_launch": int(alg[kname])}
-
-    roofline = roof(dom)
-    # the hash probe against the random-access rate measured on this box in this run
-    probe_gbs = lk_per_step * 32.0 / (stage[probe_name] * 1e-3) / 1e9
-    roofline_probe = {"kernel": "k_" + probe_name, "lookups_per_s": round(lk_per_step / (stage[probe_name] * 1e-3), 1),
-                      "achieved_sector_gbs": round(probe_gbs, 1),
-                      "note": "32 B per lookup over the kernel that holds the probe"
-                              + (" (fused with the minimizer scan and scoring)" if fused else "")}
-    if random_gbs:
-        roofline_probe["random_sector_peak_gbs"] = round(random_gbs, 1)
-        roofline_probe["frac_of_random_sector_peak"] = round(probe_gbs / random_gbs, 4)
-
+    cfg = workload_config(args)
     out = {
         "metric": METRIC, "value": round(gbp_s, 3), "unit": UNIT, "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 4),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
-        "data": "synthetic",
-        "config": {
-            "workload": "BASELINE configs[1] shape: 2x150 bp paired-end, 50% genome-derived, "
-                        "--conf 0.5, synthetic HPRC.r2-sized kraken2 table",
-            "pairs_per_step_per_gpu": n_pairs, "read_len": READ_LEN, "confidence": CONF,
-            "table_cells": capacity, "table_gib": round(capacity * 4 / 2**30, 2),
-            "table_load": round(hdr[1] / capacity, 4), "k": 35, "l": 31,
-            "genome_bases": sdb_meta["genome_bases"], "db_build_s": round(t_build, 2),
-            "l2_policy": "inputs larger than L2 (batch %.0f MB + random probes over the table)" % (total / 1e6),
-            "parallelism": f"dp{world} (read batches sharded, table replicated via NCCL broadcast)",
-        },
+        "data": "synthetic", "config": cfg,
+        "run": {"table_load": round(hdr[1] / capacity, 4), "genome_bases": int(sdb.genome_bases),
+                "db_build_s": round(t_build, 2), "db_broadcast_s": round(t_bcast, 2),
+                "parallelism": f"dp{world} (read batches sharded, table replicated via NCCL broadcast)"},
         "reads_per_s": round(reads_s, 1),
-        "stage_ms": {k_: round(v, 4) for k_, v in stage.items()},
-        "lookups_per_step": int(lk_per_step), "kernel_path": {0: "warp-per-tile", 1: "fused (phased)", 2: "fused (streaming)"}[fused_form],
-        "classified_frac": round(classified / (args.steps * n_pairs), 4),
+        "stage_ms_per_launch": {k_: round(v, 4) for k_, v in stage.items()},
+        "lookups_per_launch": int(lk_per_launch),
+        "kernel_path": {0: "warp-per-tile", 2: "streaming (k_stream_classify)"}.get(fused_form, str(fused_form)),
+        "classified_frac": round(classified / (n_timed * n_pairs), 4),
         "gpu_launches": int(launches),
-        "clocks": clocks,
-        "roofline": roofline,
-        "roofline_probe": roofline_probe,
+        "clocks": clocks, "roofline": roofline, "roofline_probe": roofline_probe,
     }
     if e2e:
         out["e2e"] = e2e
+    if parity:
+        out["parity_vs_oracle"] = parity
+    if workloads is not None:
+        out["workloads"] = workloads
 
     if world == 1 and not args.no_cpu_baseline:
-        cells = sdb.download_cells()
-        b = bufs[0]
-        h_bases = b[0][:total].cpu().numpy()
-        h_off = b[1].cpu().numpy().astype(np.uint64)
-        odb, cb = cpu_baseline(cells, sdb_meta, opts_b, taxo_b, hdr, h_bases, h_off)
-        # parity spot check of the timed configuration against the oracle
-        n = cb["pairs"]
-        got = d_call.cpu().numpy().astype(np.uint32)
-        sess.classify_device(b[0].data_ptr(), b[1].data_ptr(), n_seqs, total, d_call.data_ptr(),
-                             d_keep.data_ptr())
-        sess.sync()
-        got = d_call.cpu().numpy().astype(np.uint32)[:n]
-        out["parity_vs_oracle"] = {"pairs_checked": n,
-                                   "mismatches": int((got != cb["result"]["ext"][:n]).sum())}
+        if odb is None:
+            host_cells = sdb.download_cells()
+            odb = oracle_db_from_cells(host_cells, opts_b, taxo_b, hdr)
+        odb.confidence = CONF
+        b0 = torch.zeros(total + 64, dtype=torch.uint8, device="cuda")
+        synth.synth_reads(dev, b0.data_ptr(), d_off.data_ptr(), n_seqs, GENOME_SEED, span, seed=1000, **READS_PE)
+        torch.cuda.synchronize()
+        cb = cpu_timed_sample(odb, b0[:total].cpu().numpy(), pair_offsets(n_pairs).astype(np.uint64), 12.0,
+                              os.cpu_count() or 1)
         out["cpu_baseline"] = {
             "value": round(cb["gbp_s"], 5), "unit": UNIT, "cores": cb["cores"], "kind": "port",
-            "sample": f"first {n} pairs of the step's batch x {cb['passes']} passes, {cb['seconds']:.1f} s, "
+            "sample": f"first {cb['pairs']} pairs of one launch's batch x {cb['passes']} passes, {cb['seconds']:.1f} s, "
                       "kraken2 restatement (upstream binary unavailable offline), OpenMP",
             "reads_per_s": round(cb["reads_s"], 1),
-            "oracle_lookups_per_pair": round(cb["result"]["lookups"] / n, 2),
+            "oracle_lookups_per_pair": round(cb["result"]["lookups"] / cb["pairs"], 2),
             "oracle_sectors_per_lookup": round(cb["result"]["sectors"] / max(1, cb["result"]["lookups"]), 3),
         }
     print(json.dumps(out))
     if use_dist:
+        dist.barrier()
         dist.destroy_process_group()
     return 0
 
 
-def run_e2e(args, torch, dist, db, bufs, n_pairs, n_seqs, total, world, sampler=None):
-    """Same metric through nh_classify_batch with pinned HOST buffers: every step
-    copies its bases + offsets H2D and its calls + keep mask D2H.  Two sessions
-    on two host threads overlap one step's copies with the other's kernels."""
+def run_e2e(args, torch, dist, db, bufs, d_off, n_pairs, n_seqs, total, world, sampler=None):
+    """Same metric through nh_classify_batch with pinned HOST buffers: every launch copies its bases +
+    offsets H2D and its calls + keep mask D2H.  Two sessions on two host threads overlap one launch's
+    copies with the other's kernel.  A step is again launches_per_step launches."""
     from nohuman_b200 import Session
     n_workers = 2
+    n_host = min(4, len(bufs))  # distinct pinned host batches (1.3 GB), cycled
     sessions = [Session(db, confidence=CONF, paired=True, max_batch_bases=total + 4096,
                         max_batch_seqs=n_seqs) for _ in range(n_workers)]
     host = []
-    for b in bufs[:n_workers]:
+    ho = torch.empty(n_seqs + 1, dtype=torch.int64).pin_memory()
+    ho.copy_(d_off)
+    for b in bufs[:n_host]:
         hb = torch.empty(total, dtype=torch.uint8).pin_memory()
-        hb.copy_(b[0][:total])
-        ho = torch.empty(n_seqs + 1, dtype=torch.int64).pin_memory()
-        ho.copy_(b[1])
-        hc = torch.empty(n_pairs, dtype=torch.int32).pin_memory()
-        hk = torch.empty(n_pairs, dtype=torch.uint8).pin_memory()
-        host.append((hb, ho, hc, hk))
+        hb.copy_(b[:total])
+        host.append(hb)
+    outs = [(torch.empty(n_pairs, dtype=torch.int32).pin_memory(), torch.empty(n_pairs, dtype=torch.uint8).pin_memory())
+            for _ in range(n_workers)]
     torch.cuda.synchronize()
-    steps = max(args.steps, n_workers)
+    n_launch = args.launches_per_step
+    steps = args.steps
 
     def worker(w, n):
-        hb, ho, hc, hk = host[w]
-        for _ in range(n):
+        hc, hk = outs[w]
+        for i in range(n):
+            hb = host[(w + n_workers * i) % n_host]
             sessions[w].classify_raw(hb.data_ptr(), ho.data_ptr(), n_seqs, hc.data_ptr(), hk.data_ptr())
 
     def run(n_total):
@@ -478,13 +624,13 @@ def run_e2e(args, torch, dist, db, bufs, n_pairs, n_seqs, total, world, sampler=
         for t in ths:
             t.join()
 
-    run(max(args.warmup, n_workers))
+    run(max(args.warmup, 1) * n_workers * 2)
     if dist:
         dist.barrier()
     torch.cuda.synchronize()
     tok = sampler.mark() if sampler else None
     t0 = time.perf_counter()
-    run(steps)
+    run(steps * n_launch)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     if sampler:
@@ -495,27 +641,107 @@ def run_e2e(args, torch, dist, db, bufs, n_pairs, n_seqs, total, world, sampler=
         dt = float(t.item())
     for s in sessions:
         s.close()
-    return {"value": round(world * steps * n_pairs * 2 * READ_LEN / dt / 1e9, 3), "unit": UNIT,
-            "h2d_bytes_per_step": int(total + (n_seqs + 1) * 8), "d2h_bytes_per_step": int(n_pairs * 5),
-            "ms_per_step": round(dt / steps * 1e3, 4), "steps": steps,
-            "api": "nh_classify_batch (host buffers, pinned), 2 sessions on 2 host threads"}
+    return {"value": round(world * steps * n_launch * n_pairs * 2 * READ_LEN / dt / 1e9, 3), "unit": UNIT,
+            "h2d_bytes_per_step": int(n_launch * (total + (n_seqs + 1) * 8)), "d2h_bytes_per_step": int(n_launch * n_pairs * 5),
+            "ms_per_step": round(dt / steps * 1e3, 4), "steps": steps, "input_format": "ASCII, 1 byte per base",
+            "api": "nh_classify_batch (host buffers, pinned), 2 sessions on 2 host threads, "
+                   f"{n_host} distinct host batches cycled",
+            "why_not_packed": "a 2-bit+mask H2D format needs the host to pack ASCII first: tools/pack_bench.cc on this "
+                              "pool's 16-core host packs 73 Gbases/s with all cores (host DRAM bound), one GPU's PCIe already "
+                              "moves 51 Gbases/s of ASCII with none (DESIGN.md §4c)"}
 
 
-def reference_arm(args, torch, sdb, sdb_meta, opts_b, taxo_b, hdr, bufs):
-    """CPU implementation of the path on the host cores: the oracle port of
-    kraken2's classifier (kraken2 itself is not installable offline)."""
-    cells = sdb.download_cells()
-    b = bufs[0]
-    total = b[3]
-    h_bases = b[0][:total].cpu().numpy()
-    h_off = b[1].cpu().numpy().astype(np.uint64)
-    sdb.db.close()
-    odb, probe = cpu_baseline(cells, sdb_meta, opts_b, taxo_b, hdr, h_bases, h_off, target_s=3.0)
+def run_workloads(args, torch, dist, db, synth, Session, odb, span, rank, world, dev, peak_lk, max_over_ranks, sum_over_ranks):
+    """BASELINE configs[2] / configs[4]: device-resident timing of every shape on every rank's own batch, plus an
+    oracle parity sample of >= 20 Mbp that all ranks classify on their own replica."""
+    rows = []
+    total_target = args.workload_mbases * 1_000_000
+    for name, shape, sampler_args, conf, keep_human, paired in workload_list(args):
+        off = workload_offsets(shape, total_target, seed=7)  # same lengths on every rank, different reads
+        n = len(off) - 1
+        total = int(off[-1])
+        d_off = torch.from_numpy(off).cuda()
+        d_bases = torch.zeros(total + 64, dtype=torch.uint8, device="cuda")
+        synth.synth_reads(dev, d_bases.data_ptr(), d_off.data_ptr(), n, GENOME_SEED, span, seed=9000 + 17 * rank, **sampler_args)
+        # the parity sample: a prefix of >= 20 Mbp of a batch seeded the same on every rank
+        n_s = min(n, int(np.searchsorted(off, 20_000_000)) + 1)
+        s_total = int(off[n_s])
+        d_sample = torch.zeros(s_total + 64, dtype=torch.uint8, device="cuda")
+        synth.synth_reads(dev, d_sample.data_ptr(), d_off.data_ptr(), n_s, GENOME_SEED, span, seed=COMMON_SEED, **sampler_args)
+        torch.cuda.synchronize()
+        d_call = torch.empty(n, dtype=torch.int32, device="cuda")
+        d_keep = torch.empty(n, dtype=torch.uint8, device="cuda")
+        want = torch.zeros(n_s, dtype=torch.int32, device="cuda")
+        have_oracle = torch.tensor([1 if odb is not None else 0], dtype=torch.int32, device="cuda")
+        if rank == 0 and odb is not None:
+            odb.confidence = conf
+            r = odb.classify_batch(d_sample[:s_total].cpu().numpy(), off[:n_s + 1].astype(np.uint64), paired=paired)
+            want.copy_(torch.from_numpy(r["ext"].astype(np.int32)))
+        if dist:
+            dist.broadcast(want, 0)
+            dist.broadcast(have_oracle, 0)
+        with Session(db, confidence=conf, keep_human=keep_human, paired=paired, max_batch_bases=total + 4096,
+                     max_batch_seqs=n) as sess:
+            ext = torch.cuda.ExternalStream(sess.stream)
+            sess.classify_device(d_sample.data_ptr(), d_off.data_ptr(), n_s, s_total, d_call.data_ptr(), d_keep.data_ptr())
+            sess.sync()
+            mism = int((d_call[:n_s] != want).sum().item()) if int(have_oracle.item()) else -1
+            keep_bad = int((d_keep[:n_s] != (want != 0).to(torch.uint8)).sum().item()) if keep_human else 0
+            for _ in range(2):
+                sess.classify_device(d_bases.data_ptr(), d_off.data_ptr(), n, total, d_call.data_ptr(), d_keep.data_ptr())
+                st = sess.sync()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            if dist:
+                dist.barrier()
+            torch.cuda.synchronize()
+            reps = 4
+            fused = 0.0
+            e0.record(ext)
+            for _ in range(reps):
+                sess.classify_device(d_bases.data_ptr(), d_off.data_ptr(), n, total, d_call.data_ptr(), d_keep.data_ptr())
+                st = sess.sync()
+                fused += st.ms_minimizer
+            e1.record(ext)
+            torch.cuda.synchronize()
+            ms = max_over_ranks(e0.elapsed_time(e1) / reps)
+            ms_fused = max_over_ranks(fused / reps)
+        lk = int(st.n_lookups)
+        row = {"workload": name, "reads_per_gpu": n, "bases_per_gpu": total, "ms_per_launch": round(ms, 4),
+               "gbp_s": round(world * total / ms / 1e6, 2), "reads_per_s": round(world * n / ms * 1e3, 1),
+               "lookups_per_s": round(world * lk / ms_fused * 1e3, 1),
+               "frac_of_request_ceiling": round(lk / (ms_fused * 1e-3) / peak_lk, 4) if peak_lk else None,
+               "stage_ms": {"plan": round(st.ms_plan, 4), "stream_classify": round(st.ms_minimizer, 4),
+                            "score_deferred": round(st.ms_score, 4)},
+               "classified_frac": round(st.n_classified / n, 4),
+               "parity_vs_oracle": {"sample_reads": n_s, "sample_bases": s_total, "ranks_checked": sum_over_ranks(1),
+                                    "mismatches": sum_over_ranks(max(mism, 0)) if mism >= 0 else None,
+                                    "keep_mask_mismatches": sum_over_ranks(keep_bad)}}
+        rows.append(row)
+        del d_bases, d_sample, d_call, d_keep, d_off, want
+        torch.cuda.empty_cache()
+    return rows
+
+
+def reference_arm(args):
+    """CPU implementation of the path on the host cores: the oracle port of kraken2's classifier
+    (kraken2 itself is not installable offline), on the same workload.  No torch, no CUDA library:
+    the table and the reads come from the generator's CPU twin (oracle/k2_synth.c)."""
+    from oracle import k2synth
+    capacity = 1 << args.capacity_log2
+    cores = os.cpu_count() or 1
+    t0 = time.perf_counter()
+    odb, meta = k2synth.build_synthetic_db(capacity, genome_seed=GENOME_SEED, threads=cores)
+    t_build = time.perf_counter() - t0
+    odb.confidence = CONF
+    span = read_span(capacity)
+    n_pairs = args.pairs_per_launch
+    off = pair_offsets(n_pairs).astype(np.uint64)
+    bases = k2synth.synth_reads(off, GENOME_SEED, span, seed=1000, threads=cores, **READS_PE)  # rank 0's first batch
+    probe = cpu_timed_sample(odb, bases, off, 1.0, cores)
     n = args.ref_pairs_per_step or probe["pairs"]
-    n = min(n, (len(h_off) - 1) // 2)
-    o = h_off[:2 * n + 1]
-    bb = h_bases[:int(o[-1])]
-    cores = probe["cores"]
+    n = min(n, n_pairs)
+    o = off[:2 * n + 1]
+    bb = bases[:int(o[-1])]
     for _ in range(max(1, min(args.warmup, 2))):
         odb.classify_batch(bb, o, paired=True, threads=cores)
     t0 = time.perf_counter()
@@ -527,17 +753,13 @@ def reference_arm(args, torch, sdb, sdb_meta, opts_b, taxo_b, hdr, bufs):
         "impl": "reference", "metric": METRIC, "value": round(gbp_s, 5), "unit": UNIT,
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(dt / args.steps * 1e3, 3), "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": {
-            "workload": "BASELINE configs[1] shape: 2x150 bp paired-end, 50% genome-derived, "
-                        "--conf 0.5, synthetic HPRC.r2-sized kraken2 table",
-            "pairs_per_step": n, "read_len": READ_LEN, "confidence": CONF,
-            "table_cells": hdr[0], "table_load": round(hdr[1] / hdr[0], 4),
-        },
+        "vs_baseline": None, "dtype": "u64", "data": "synthetic", "config": workload_config(args),
+        "run": {"table_load": round(meta["hash_header"][1] / capacity, 4), "genome_bases": meta["genome_bases"],
+                "db_build_s": round(t_build, 2), "table_built_by": "oracle/k2_synth.c on the host cores"},
         "reads_per_s": round(args.steps * 2 * n / dt, 1),
         "cpu_baseline": {"value": round(gbp_s, 5), "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{n} pairs per step x {args.steps} steps; kraken2 restatement "
-                                   "(upstream binary unavailable offline), OpenMP on all host cores"},
+                         "sample": f"{n} pairs per step (a bounded sample of the 10M-pair step) x {args.steps} steps; kraken2 "
+                                   "restatement (upstream binary unavailable offline), OpenMP on all host cores"},
         "e2e": {"value": round(gbp_s, 5), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }

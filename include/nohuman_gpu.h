@@ -93,7 +93,8 @@ typedef struct {
   float ms_plan, ms_minimizer, ms_probe, ms_score;
   float ms_h2d, ms_d2h;
   uint32_t gpu_launches;   /* kernels launched for this batch */
-  uint32_t fused_kernel;   /* 0: warp-per-tile kernels, 1: k_scan_probe_score, 2: k_stream_classify */
+  uint32_t fused_kernel;   /* 0: warp-per-tile kernels, 2: k_stream_classify */
+  uint64_t n_sector_reads; /* k_stream_classify: 32-byte table sectors requested (lookups + chain continuations) */
 } nh_batch_stats_t;
 
 typedef struct {
@@ -219,6 +220,14 @@ int nh_debug_last_batch(nh_session *s, uint32_t *out_call_internal, uint32_t *ou
  * n_reads sectors per launch, `iters` launches; returns the best launch in
  * GB/s of sectors (the random-access HBM roofline the probe is held to). */
 int nh_bench_random_gather(nh_db *db, uint64_t n_reads, int iters, double *out_gbs);
+/* The probe's own access pattern over the resident table, nothing else: every chain reads a random
+ * sector and, with probability p_continue, the adjacent one once the first has arrived; `lanes`
+ * (1, 2, 4) lanes share an item and read an aligned block of that many sectors in one instruction;
+ * sm_window_bytes > 0 confines each SM to its own window.  Returns the best of `iters` launches as
+ * items (lookups) per second and table requests per second. */
+int nh_bench_probe_pattern(nh_db *db, int lanes, double p_continue, uint64_t sm_window_bytes,
+                           uint32_t items_per_chain, int iters, double *out_items_per_s,
+                           double *out_requests_per_s);
 
 #ifdef __cplusplus
 }

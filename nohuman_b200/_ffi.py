@@ -59,6 +59,7 @@ class BatchStats(C.Structure):
         ("ms_plan", C.c_float), ("ms_minimizer", C.c_float), ("ms_probe", C.c_float),
         ("ms_score", C.c_float), ("ms_h2d", C.c_float), ("ms_d2h", C.c_float),
         ("gpu_launches", C.c_uint32), ("fused_kernel", C.c_uint32),
+        ("n_sector_reads", C.c_uint64),
     ]
 
     def as_dict(self):
@@ -109,6 +110,8 @@ SYMBOLS = {
     "nh_debug_probe": (_i32, [_vp, _vp, _u64, _vp]),
     "nh_debug_last_batch": (_i32, [_vp, _vp, _vp, _vp, _u64]),
     "nh_bench_random_gather": (_i32, [_vp, _u64, _i32, C.POINTER(C.c_double)]),
+    "nh_bench_probe_pattern": (_i32, [_vp, _i32, C.c_double, _u64, C.c_uint32, _i32, C.POINTER(C.c_double),
+                                      C.POINTER(C.c_double)]),
 }
 
 _lib = None

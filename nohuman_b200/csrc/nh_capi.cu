@@ -732,6 +732,7 @@ extern "C" int nh_session_sync(nh_session *s, nh_batch_stats_t *stats) {
       stats->n_bases = s->last_bases;
       stats->n_tiles = c.n_tiles;
       stats->n_lookups = c.n_lookups;
+      stats->n_sector_reads = c.n_sector_reads;
       cudaEventElapsedTime(&stats->ms_plan, s->ev[EV_PLAN0], s->ev[EV_MIN0]);
       cudaEventElapsedTime(&stats->ms_minimizer, s->ev[EV_MIN0], s->ev[EV_PROBE0]);
       cudaEventElapsedTime(&stats->ms_probe, s->ev[EV_PROBE0], s->ev[EV_SCORE0]);
@@ -910,34 +911,63 @@ extern "C" int nh_last_batch_runs(nh_session *s, uint64_t n_seqs, uint32_t *seq_
 }
 
 /* ------------------------------------------------------------------ */
-extern "C" int nh_bench_random_gather(nh_db *db, uint64_t n_reads, int iters, double *out_gbs) {
-  if (!db || !out_gbs || iters < 1) return nh_set_error(NH_ERR_INVALID, "bad argument");
+extern "C" int nh_bench_probe_pattern(nh_db *db, int lanes, double p_continue, uint64_t sm_window_bytes,
+                                      uint32_t items_per_chain, int iters, double *out_items_per_s,
+                                      double *out_requests_per_s) {
+  if (!db || !out_items_per_s || !out_requests_per_s || iters < 1 || items_per_chain < 1 ||
+      (lanes != 1 && lanes != 2 && lanes != 4) || !(p_continue >= 0.0 && p_continue < 1.0))
+    return nh_set_error(NH_ERR_INVALID, "bad argument");
   CUDA_TRY(cudaSetDevice(db->info.device));
   const uint64_t n_sectors = db->info.capacity / 8;
-  if (n_sectors == 0) return nh_set_error(NH_ERR_INVALID, "table too small");
+  if (n_sectors < 64 || (sm_window_bytes && sm_window_bytes / 32 > n_sectors))
+    return nh_set_error(NH_ERR_INVALID, "table too small");
   uint32_t *sink = nullptr;
+  unsigned long long *d_cnt = nullptr;
   CUDA_TRY(cudaMalloc(&sink, 64));
+  CUDA_TRY(cudaMalloc(&d_cnt, 16));
   cudaStream_t st;
   CUDA_TRY(cudaStreamCreate(&st));
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0);
   cudaEventCreate(&e1);
-  float best = 1e30f;
+  const uint32_t p_thresh = (uint32_t)(p_continue * 4294967296.0);
+  double best_items = 0, best_req = 0;
   for (int i = 0; i < iters + 1; i++) { /* first launch is warm-up */
+    cudaMemsetAsync(d_cnt, 0, 16, st);
     cudaEventRecord(e0, st);
-    nh_launch_random_gather(db->d_cells, n_sectors, n_reads, 0x1234567ULL * (uint64_t)(i + 1), sink,
-                            db->sm_count, st);
+    nh_launch_probe_pattern(db->d_cells, n_sectors, lanes, items_per_chain, p_thresh, 0x1234567ULL * (uint64_t)(i + 1),
+                            sm_window_bytes / 32, d_cnt, sink, db->sm_count, st);
     cudaEventRecord(e1, st);
-    cudaEventSynchronize(e1);
+    unsigned long long h[2] = {0, 0};
+    cudaMemcpyAsync(h, d_cnt, 16, cudaMemcpyDeviceToHost, st);
+    cudaStreamSynchronize(st);
     float ms = 0;
     cudaEventElapsedTime(&ms, e0, e1);
-    if (i > 0 && ms < best) best = ms;
+    if (i > 0 && ms > 0 && (double)h[0] / ms > best_items) {
+      best_items = (double)h[0] / ms;
+      best_req = (double)h[1] / ms;
+    }
   }
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
   cudaStreamDestroy(st);
   cudaFree(sink);
+  cudaFree(d_cnt);
   CUDA_TRY(cudaGetLastError());
-  *out_gbs = (double)n_reads * 32.0 / ((double)best * 1e-3) / 1e9;
+  *out_items_per_s = best_items * 1e3;
+  *out_requests_per_s = best_req * 1e3;
+  return NH_OK;
+}
+
+/* the p = 0 case of the pattern above, in GB/s of 32-byte sectors (kept for callers of ABI 1) */
+extern "C" int nh_bench_random_gather(nh_db *db, uint64_t n_reads, int iters, double *out_gbs) {
+  if (!db || !out_gbs || iters < 1) return nh_set_error(NH_ERR_INVALID, "bad argument");
+  const uint64_t chains = (uint64_t)db->sm_count * 8 * 256 * 4;
+  uint64_t per = n_reads / chains;
+  if (per < 1) per = 1;
+  double items = 0, req = 0;
+  int rc = nh_bench_probe_pattern(db, 1, 0.0, 0, (uint32_t)per, iters, &items, &req);
+  if (rc) return rc;
+  *out_gbs = req * 32.0 / 1e9;
   return NH_OK;
 }

@@ -130,6 +130,7 @@ k_plan_scan(uint64_t *__restrict__ block_sums, uint32_t nb, NhCounters *__restri
     counters->error = 0;
     counters->n_deferred = 0;
     counters->next_group = 0;
+    counters->n_sector_reads = 0;
   }
 }
 
@@ -759,8 +760,8 @@ k_score_big(const NhDbParams db, const NhBatchPtrs b, const NhScoreParams sp) {
 
 template <bool EMIT>
 struct __align__(16) StreamWarpSmem {
-  uint64_t pq_key[NH_PQ_SLOTS];          /* closed runs waiting to be probed (ring) */
-  uint16_t pq_meta[NH_PQ_SLOTS];         /* tile's lane | k-mer count << 5 | NH_META_FIRST */
+  uint4 pq[NH_PQ_SLOTS];                 /* closed runs waiting to be probed (ring): key lo, key hi, meta, lookup slot;
+                                          * meta = tile's lane | k-mer count << 5 | NH_META_FIRST */
   uint32_t q_unit[32];                   /* probe chains that continue into the next sector (at most one per lane) */
   uint32_t q_ckey[32];
   uint32_t q_aux[32];                    /* pq_meta | sectors visited << 16 */
@@ -776,8 +777,7 @@ struct __align__(16) StreamWarpSmem {
   uint64_t bbar[2], sbar;
   __align__(16) uint8_t bchunk[2][32 * NH_BCHUNK_STRIDE];
   __align__(16) uint32_t sect[32 * 8];
-  uint32_t pq_slot[EMIT ? NH_PQ_SLOTS : 1]; /* per-read output only: where the lookup's taxon goes */
-  uint32_t q_slot[EMIT ? 32 : 1];
+  uint32_t q_slot[EMIT ? 32 : 1]; /* per-read output only: where the lookup's taxon goes */
 };
 
 /* 3 blocks of 8 warps per SM (up to 85 registers): the overlap of table latency and scan happens
@@ -804,6 +804,10 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 /* 16 bytes global -> shared without a register or a load scoreboard in between (LDGSTS, L2 only) */
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+/* the same with only the first n_src bytes taken from global memory and the rest zero-filled */
+__device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void *src, uint32_t n_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(n_src) : "memory");
 }
 /* the same for a table sector half: a miss fills 64 bytes of L2, not the default 128 */
 __device__ __forceinline__ void cp_async16_l2_64(uint32_t dst, const void *src) {
@@ -836,7 +840,9 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
 #define NH_STREAM_CHECK_MASK 1 /* probe check after bases with (j & mask) == mask: 1 -> every 2nd base */
 #endif
 
-template <int W, bool DBG, bool REV0, bool EMIT>
+/* KL = 1: kraken2's default k = 35, l = 31 compiled in (shift counts and thresholds become
+ * immediates); KL = 0: any k, l with k - l + 1 = W, read from the database */
+template <int W, int KL, bool DBG, bool REV0, bool EMIT>
 __global__ void __launch_bounds__(NH_BLOCK_THREADS, NH_STREAM_MIN_BLOCKS)
 k_stream_classify(const NhDbParams db, const NhBatchPtrs b, const NhScoreParams sp) {
   static_assert(W == 5, "the scan consumes one 4-byte word per ring rotation");
@@ -857,7 +863,8 @@ k_stream_classify(const NhDbParams db, const NhBatchPtrs b, const NhScoreParams 
   const uint32_t lane_lt = (1u << lane) - 1u;
   Smem &sm = s_warps[warp];
   const uint32_t n_tiles = b.counters->n_tiles;
-  const int k = db.k, l = db.l;
+  const int k = KL ? 35 : db.k, l = KL ? 31 : db.l;
+  const uint32_t amb_span = KL ? 34u : (uint32_t)db.amb_span;
   const uint64_t lmask = (1ULL << (2 * l)) - 1ULL;
   const uint32_t rc_shift = 2u * (uint32_t)(l - 1);
   const uint32_t n_sectors = (uint32_t)((db.capacity + 7ULL) >> 3); /* nh_fused_supported: capacity < 2^35 */
@@ -866,7 +873,7 @@ k_stream_classify(const NhDbParams db, const NhBatchPtrs b, const NhScoreParams 
   const uint32_t last_range = (db.capacity & 7ULL) ? (1u << (uint32_t)(db.capacity & 7ULL)) - 1u : 0xFFu;
   /* probe-chain guard for a table without any empty cell (never a real database) */
   const uint32_t max_visits = n_sectors + 1u < 0xFFFFu ? n_sectors + 1u : 0xFFFFu;
-  uint32_t tot_lookups = 0, tot_classified = 0, tot_kept = 0;
+  uint32_t tot_lookups = 0, tot_sectors = 0, tot_classified = 0, tot_kept = 0;
 
   const uint32_t bar0 = smem_addr(&sm.bbar[0]);
   const uint32_t win0 = smem_addr(&sm.bchunk[0][lane * NH_BCHUNK_STRIDE]);
@@ -913,6 +920,8 @@ k_stream_classify(const NhDbParams db, const NhBatchPtrs b, const NhScoreParams 
 
     /* warp-uniform queue state */
     uint32_t pq_head = 0, pq_n = 0, cq_n = 0;
+    uint32_t n_popped = 0; /* fresh lookups handed to the probe = distinct-consecutive minimizers of the group */
+    uint32_t n_conts = 0;  /* chain continuations: a second, third ... sector of a lookup */
     /* the lookup this lane has in flight: its sector lands in sm.sect, looked at in the next round */
     uint32_t f_unit = 0, f_ckey = 0, f_slot = 0, f_aux = NH_AUX_NONE, f_start = 0;
     bool any_inflight = false; /* warp-uniform */
@@ -999,10 +1008,10 @@ k_stream_classify(const NhDbParams db, const NhBatchPtrs b, const NhScoreParams 
         f_aux = sm.q_aux[lane];
         if (EMIT) f_slot = sm.q_slot[lane];
       } else if (lane - n_cq < n_pq) {
-        const uint32_t i = (pq_head + (lane - n_cq)) & (NH_PQ_SLOTS - 1u);
-        const uint64_t h = nh_fmix64(sm.pq_key[i]);
-        if (EMIT) f_slot = sm.pq_slot[i];
-        const uint32_t meta = sm.pq_meta[i];
+        const uint4 e = sm.pq[(pq_head + (lane - n_cq)) & (NH_PQ_SLOTS - 1u)];
+        const uint64_t h = nh_fmix64(((uint64_t)e.y << 32) | e.x);
+        if (EMIT) f_slot = e.w;
+        const uint32_t meta = e.z;
         if (db.min_hash && h < db.min_hash) {
           /* below minimum_acceptable_hash_value: kraken2 skips the lookup, taxon 0 */
           if (EMIT) b.lk_taxon[f_slot] = 0u;
@@ -1017,6 +1026,8 @@ k_stream_classify(const NhDbParams db, const NhBatchPtrs b, const NhScoreParams 
       cq_n = 0;
       pq_head = (pq_head + n_pq) & (NH_PQ_SLOTS - 1u);
       pq_n -= n_pq;
+      n_popped += n_pq;
+      n_conts += n_cq;
       any_inflight = (n_cq + n_pq) != 0u;
       if (any_inflight) {
         /* lane pairs fetch the two 16-byte halves of one sector with ONE instruction, so a sector
@@ -1035,8 +1046,9 @@ k_stream_classify(const NhDbParams db, const NhBatchPtrs b, const NhScoreParams 
     };
 
     /* ---------------- scan, feeding the probe ---------------- */
-    uint32_t n_runs = 0;
-    uint64_t last = NH_NONE64; /* minimizer of the open run */
+    uint32_t n_runs = 0;           /* EMIT and DBG only: runs this lane has closed */
+    uint32_t first_flag = NH_META_FIRST; /* cleared by the lane's first run */
+    uint64_t last = NH_NONE64;     /* minimizer of the open run */
     {
       uint64_t so = 0;
       uint32_t nb = 0; /* bases of this lane's tile */
@@ -1065,25 +1077,31 @@ k_stream_classify(const NhDbParams db, const NhBatchPtrs b, const NhScoreParams 
       const uint32_t first_pos = mis + (uint32_t)(k - 1);
       const uint32_t end_idx = mis + nb;
 
-      /* a closed run goes to the shared queue */
+      /* a closed run goes to the shared queue as one 16-byte entry */
       auto emit = [&](bool pred, uint64_t key, uint32_t count) {
         const uint32_t emask = __ballot_sync(FULL_MASK, pred);
         if (pred) {
-          const uint32_t i = (pq_head + pq_n + __popc(emask & lane_lt)) & (NH_PQ_SLOTS - 1u);
-          sm.pq_key[i] = key;
-          sm.pq_meta[i] = (uint16_t)(lane | (count << 5) | (n_runs == 0u ? NH_META_FIRST : 0u));
-          if (n_runs == 0u) sm.first_min[lane] = key;
+          uint4 e;
+          e.x = (uint32_t)key;
+          e.y = (uint32_t)(key >> 32);
+          e.z = lane | (count << 5) | first_flag;
+          e.w = 0;
           if (EMIT) {
-            const uint32_t slot = t.slot + n_runs;
-            sm.pq_slot[i] = slot;
-            b.lk_cnt[slot] = (uint16_t)count;
+            e.w = t.slot + n_runs;
+            b.lk_cnt[e.w] = (uint16_t)count;
           }
-          n_runs++;
+          sm.pq[(pq_head + pq_n + __popc(emask & lane_lt)) & (NH_PQ_SLOTS - 1u)] = e;
+          if (first_flag) sm.first_min[lane] = key;
+          first_flag = 0;
+          if (EMIT || DBG) n_runs++;
         }
         pq_n += __popc(emask);
       };
 
-      /* four bases (one 4-byte word of the word-aligned stream, first base at stream index base_i) */
+      /* Four bases (one 4-byte word of the word-aligned stream, first base at stream index base_i).
+       * Bytes outside the tile never get here as bases: the staging zero-fills what lies past the
+       * tile's end and the head of the first word is cleared below, and a zero byte is an ambiguous
+       * base - it resets the l-mer and cannot end a k-mer. */
       auto scan_word = [&](const uint32_t word, const uint32_t base_i) {
         uint32_t ambs;
         const uint32_t codes = nh_pack4(word, &ambs); /* first base in bits 7..6 */
@@ -1091,9 +1109,7 @@ k_stream_classify(const NhDbParams db, const NhBatchPtrs b, const NhScoreParams 
         for (int j = 0; j < 4; j++) {
           const uint32_t i = base_i + (uint32_t)j; /* index in the word-aligned stream */
           const uint32_t cc = (codes >> (6u - 2u * (uint32_t)j)) & 3u;
-          const bool inside = i >= mis && i < end_idx;
-          /* bytes outside the tile count as ambiguous: they reset the l-mer and never reach a position */
-          const bool amb = ((ambs >> j) & 1u) || !inside;
+          const bool amb = (ambs >> j) & 1u;
           fwd = ((fwd << 2) | cc) & lmask;
           rc = (rc >> 2) | ((uint64_t)(3u - cc) << rc_shift);
           c_run = amb ? 0u : c_run + 1u;
@@ -1111,10 +1127,10 @@ k_stream_classify(const NhDbParams db, const NhBatchPtrs b, const NhScoreParams 
 #pragma unroll
           for (int r = 3; r > 0; r--) ring[r] = ring[r - 1];
           ring[0] = cand;
-          const bool at_pos = inside && i >= first_pos;
-          const bool nonamb = at_pos && c_run >= (uint32_t)db.amb_span;
+          /* c_run counts from the tile's first base, so before first_pos a k-mer cannot have ended */
+          const bool nonamb = i >= first_pos && c_run >= amb_span;
           const uint64_t mz = m ^ db.toggle;
-          if (DBG && at_pos) { /* per-position output for nh_debug_minimizers */
+          if (DBG && i >= first_pos && i < end_idx) { /* per-position output for nh_debug_minimizers */
             const uint64_t o = dbg_base + (i - first_pos);
             b.dbg_pos_min[o] = mz;
             b.dbg_pos_ambig[o] = nonamb ? 0 : 1;
@@ -1133,15 +1149,20 @@ k_stream_classify(const NhDbParams db, const NhBatchPtrs b, const NhScoreParams 
       const uint8_t *q = g - mis;
       const uint32_t a16 = (uint32_t)((uintptr_t)q & 15u);
       const uint8_t *src0 = q - a16;
-      const uint32_t my_bytes = my_words ? a16 + my_words * 4u : 0u;
+      const uint32_t my_bytes = have ? a16 + mis + nb : 0u; /* from src0 to the tile's last base */
       const uint32_t n_chunks = (max_words + NH_BCHUNK_WORDS - 1u) / NH_BCHUNK_WORDS;
       auto stage = [&](const uint32_t ch) {
         const uint32_t buf = ch & 1u;
         const uint32_t lo = ch * (NH_BCHUNK_WORDS * 4u);
         const uint32_t dst = win0 + buf * (32u * NH_BCHUNK_STRIDE);
 #pragma unroll
-        for (uint32_t pc = 0; pc < NH_BCHUNK_STRIDE; pc += 16u)
-          if (lo + pc < my_bytes) cp_async16(dst + pc, src0 + lo + pc);
+        for (uint32_t pc = 0; pc < NH_BCHUNK_STRIDE; pc += 16u) {
+          /* bytes past the tile's end arrive as zeros (ambiguous bases); a lane whose tile is over keeps
+           * clearing its window, so what it scans while longer tiles finish can never close a run */
+          const uint32_t at = lo + pc;
+          const uint32_t n_src = at < my_bytes ? (my_bytes - at < 16u ? my_bytes - at : 16u) : 0u;
+          cp_async16_zfill(dst + pc, n_src ? src0 + at : src0, n_src);
+        }
         cp_async_arrive(bar0 + buf * 8u);
       };
       if (n_chunks) stage(0u);
@@ -1154,6 +1175,7 @@ k_stream_classify(const NhDbParams db, const NhBatchPtrs b, const NhScoreParams 
         const uint32_t w0 = ch * NH_BCHUNK_WORDS;
         const uint32_t wn = max_words - w0 < NH_BCHUNK_WORDS ? max_words - w0 : NH_BCHUNK_WORDS;
         uint32_t w_next = lds_u32(wbase);
+        if (ch == 0u) w_next &= 0xFFFFFFFFu << (8u * mis); /* the bytes before the tile's first base */
 #pragma unroll 1
         for (uint32_t w = 0; w < wn; w++) {
           const uint32_t word = w_next;
@@ -1164,24 +1186,26 @@ k_stream_classify(const NhDbParams db, const NhBatchPtrs b, const NhScoreParams 
       }
       emit(cnt != 0u, last, cnt);
     }
+    const bool has_runs = first_flag == 0u;
     if (EMIT && have) {
       NhTileOut o;
       o.lk_off = t.slot;
       o.lk_cnt = n_runs;
       b.tile_out[tile] = o;
     }
-    tot_lookups += n_runs;
-    if (n_runs) sm.last_min[lane] = last; /* the run closed last carried `last` */
+    if (has_runs) sm.last_min[lane] = last; /* the run closed last carried `last` */
     /* drain: whatever is waiting or in flight */
     while (pq_n + cq_n != 0u || any_inflight) probe_round();
+    tot_lookups += n_popped; /* warp-uniform; added once per warp below */
+    tot_sectors += n_popped + n_conts;
 
     /* ---------------- tile borders inside a unit scored here ---------------- */
     /* A tile starts with a fresh lookup even when its first minimizer equals the last one of the
      * tile before it in the same sequence; upstream counts that as ONE hit group (its
      * last_minimizer lives per mate, ambiguous stretches included). */
     {
-      const uint32_t has_mask = __ballot_sync(FULL_MASK, n_runs != 0u);
-      if (have && kind != NH_ROLE_DEFERRED && t.pos_begin != 0u && n_runs != 0u && ((sm.first_hit >> lane) & 1u)) {
+      const uint32_t has_mask = __ballot_sync(FULL_MASK, has_runs);
+      if (have && kind != NH_ROLE_DEFERRED && t.pos_begin != 0u && has_runs && ((sm.first_hit >> lane) & 1u)) {
         const uint32_t seq_lane = lane - t.pos_begin / (uint32_t)db.tile_pos; /* lane of the sequence's first tile */
         const uint32_t cand = has_mask & lane_lt & ~((1u << seq_lane) - 1u);
         if (cand) {
@@ -1196,10 +1220,10 @@ k_stream_classify(const NhDbParams db, const NhBatchPtrs b, const NhScoreParams 
     if (have && kind == NH_ROLE_DEFERRED) {
       const bool ovf = (sm.overflow >> lane) & 1u;
       NhTileSum ts;
-      ts.first_min = n_runs ? sm.first_min[lane] : NH_NONE64;
-      ts.last_min = n_runs ? last : NH_NONE64;
+      ts.first_min = has_runs ? sm.first_min[lane] : NH_NONE64;
+      ts.last_min = has_runs ? last : NH_NONE64;
       ts.groups = sm.groups[lane];
-      ts.flags = (n_runs ? NH_TILE_HAS : 0u) | (((sm.first_hit >> lane) & 1u) ? NH_TILE_FIRST_HIT : 0u) |
+      ts.flags = (has_runs ? NH_TILE_HAS : 0u) | (((sm.first_hit >> lane) & 1u) ? NH_TILE_FIRST_HIT : 0u) |
                  (ovf ? NH_TILE_OVERFLOW : 0u);
       b.tile_sum[tile] = ts;
       if (!ovf) {
@@ -1263,11 +1287,11 @@ k_stream_classify(const NhDbParams db, const NhBatchPtrs b, const NhScoreParams 
     }
     __syncwarp();
   }
-  tot_lookups = warp_sum_u32(tot_lookups);
   tot_classified = warp_sum_u32(tot_classified);
   tot_kept = warp_sum_u32(tot_kept);
   if (lane == 0) {
     if (tot_lookups) atomicAdd(&b.counters->n_lookups, tot_lookups);
+    if (tot_sectors) atomicAdd(&b.counters->n_sector_reads, tot_sectors);
     if (tot_classified) atomicAdd(&b.counters->n_classified, tot_classified);
     if (tot_kept) atomicAdd(&b.counters->n_kept, tot_kept);
   }
@@ -1297,21 +1321,85 @@ k_gather_runs(const NhDbParams db, const NhBatchPtrs b, uint32_t *__restrict__ r
 }
 
 /* ------------------------------------------------------------------ */
-/* roofline helper: uniformly random aligned 32-byte sector reads       */
-
+/* roofline helper: the probe's access pattern and nothing else             */
+/*
+ * What bounds the hash probe on B200 is the rate of random table requests
+ * (address translation), so the ceiling the streaming kernel is
+ * held to is measured with its own access pattern: every lane keeps DEPTH
+ * independent probe chains going; a chain reads a random 32-byte sector and,
+ * with probability p (the table's chain-spill rate, 0.41 at load 0.7), the
+ * ADJACENT sector - but only after the first one has arrived, exactly like a
+ * continuation that waits one probe round in k_stream_classify.  G lanes can
+ * share one item and read G adjacent sectors of an aligned 32*G-byte block
+ * with one instruction (a request is a warp instruction x 128-byte line).
+ * SMWIN > 0 confines every SM to its own window of that many bytes (perfect
+ * page locality: not reachable by a hash table, reported as a curiosity).
+ * No hashing of k-mers, no scan, no scoring: whatever this reaches is an upper
+ * bound for any kernel that makes the same table requests.
+ */
+template <int G, int DEPTH>
 __global__ void __launch_bounds__(256)
-k_random_gather(const uint32_t *__restrict__ cells, uint64_t n_sectors, uint64_t n_reads,
-                uint64_t seed, uint32_t *__restrict__ sink) {
-  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+k_probe_pattern(const uint32_t *__restrict__ cells, uint64_t n_sectors, uint32_t items_per_chain,
+                uint32_t p_thresh /* of 2^32 */, uint64_t seed, uint64_t sm_window_sectors,
+                unsigned long long *__restrict__ counters /* [0] items, [1] requests */, uint32_t *__restrict__ sink) {
+  const uint32_t lane = lane_id();
+  const uint32_t sub = lane % G;
+  const uint64_t chain0 = (((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) / G) * DEPTH;
+  uint64_t win_base = 0, win_size = n_sectors / G; /* in blocks of G sectors */
+  if (sm_window_sectors) {
+    uint32_t smid;
+    asm("mov.u32 %0, %%smid;" : "=r"(smid));
+    win_size = sm_window_sectors / G;
+    const uint64_t n_win = (n_sectors / G) / win_size;
+    win_base = (uint64_t)(smid % (uint32_t)(n_win ? n_win : 1)) * win_size;
+  }
   uint32_t acc = 0;
-  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_reads; i += stride) {
-    const uint64_t h = nh_fmix64(i + seed);
-    const uint64_t sec = __umul64hi(h, n_sectors);
-    uint32_t c[8];
-    ld_sector(cells + sec * 8ULL, c);
-    acc ^= c[0] ^ c[1] ^ c[2] ^ c[3] ^ c[4] ^ c[5] ^ c[6] ^ c[7];
+  uint32_t c[DEPTH][8];
+  uint64_t blk[DEPTH];    /* block of G sectors the chain reads next / has in flight */
+  uint32_t left[DEPTH];   /* items the chain still has to start */
+  uint32_t cont[DEPTH];   /* the request in flight is a continuation */
+  unsigned long long items = 0, requests = 0;
+#pragma unroll
+  for (int d = 0; d < DEPTH; d++) {
+    const uint64_t h = nh_fmix64(seed + (chain0 + d) * 0x9E3779B97F4A7C15ULL);
+    blk[d] = win_base + __umul64hi(h, win_size);
+    left[d] = items_per_chain;
+    cont[d] = 0;
+    ld_sector(cells + (blk[d] * G + sub) * 8ULL, c[d]);
+  }
+  bool busy = true;
+  for (uint32_t it = 1; busy; it++) {
+    busy = false;
+#pragma unroll
+    for (int d = 0; d < DEPTH; d++) {
+      if (left[d] == 0u) continue;
+      busy = true;
+      /* the data in flight decides what the chain does next, as a probe's sector does */
+      const uint32_t x = c[d][0] ^ c[d][1] ^ c[d][2] ^ c[d][3] ^ c[d][4] ^ c[d][5] ^ c[d][6] ^ c[d][7];
+      acc ^= x;
+      requests++;
+      const uint64_t h = nh_fmix64(seed ^ ((chain0 + d) << 20) ^ it ^ (uint64_t)(x & 1u) << 63);
+      if (!cont[d] && (uint32_t)h < p_thresh) {
+        cont[d] = 1;
+        blk[d] = blk[d] + 1 < win_base + win_size ? blk[d] + 1 : win_base;
+      } else {
+        cont[d] = 0;
+        items++;
+        if (--left[d] == 0u) continue;
+        blk[d] = win_base + __umul64hi(h, win_size);
+      }
+      ld_sector(cells + (blk[d] * G + sub) * 8ULL, c[d]);
+    }
   }
   if (acc == 0x9E3779B9u) sink[0] = acc; /* keeps the loads alive */
+  if (sub == 0) {
+    items = __reduce_add_sync(__activemask(), (uint32_t)items);
+    requests = __reduce_add_sync(__activemask(), (uint32_t)requests);
+    if (lane == 0) {
+      atomicAdd(&counters[0], items);
+      atomicAdd(&counters[1], requests);
+    }
+  }
 }
 
 /* ------------------------------------------------------------------ */
@@ -1331,16 +1419,17 @@ cudaError_t nh_kernels_init(void) {
                            NH_SMEM_PARENT_MAX * 4 + NH_WARPS_PER_BLOCK * NH_WARP_HASH_SLOTS * 8);
   if (e != cudaSuccess) return e;
   const int smax = (int)stream_smem_bytes<false>(NH_SMEM_PARENT_MAX), smax_emit = (int)stream_smem_bytes<true>(NH_SMEM_PARENT_MAX);
-  e = cudaFuncSetAttribute(k_stream_classify<5, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smax);
+#define NH_SET_SMEM(kern, bytes)                                                             \
+  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);       \
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(k_stream_classify<5, false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smax);
-  if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(k_stream_classify<5, true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smax);
-  if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(k_stream_classify<5, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smax_emit);
-  if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(k_stream_classify<5, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smax_emit);
-  if (e != cudaSuccess) return e;
+  NH_SET_SMEM((k_stream_classify<5, 1, false, false, false>), smax)
+  NH_SET_SMEM((k_stream_classify<5, 1, false, false, true>), smax_emit)
+  NH_SET_SMEM((k_stream_classify<5, 0, false, false, false>), smax)
+  NH_SET_SMEM((k_stream_classify<5, 0, false, true, false>), smax)
+  NH_SET_SMEM((k_stream_classify<5, 0, true, false, false>), smax)
+  NH_SET_SMEM((k_stream_classify<5, 0, false, false, true>), smax_emit)
+  NH_SET_SMEM((k_stream_classify<5, 0, false, true, true>), smax_emit)
+#undef NH_SET_SMEM
   return cudaSuccess;
 }
 
@@ -1368,16 +1457,23 @@ int nh_launch_stream(const NhDbParams &db, const NhBatchPtrs &b, const NhScorePa
   if (grid == 0) grid = 1;
   const bool emit = b.emit_all_taxa != 0;
   const size_t smem = emit ? stream_smem_bytes<true>(db.node_count) : stream_smem_bytes<false>(db.node_count);
-  if (b.dbg_pos_min != nullptr) /* nh_debug_minimizers (sessions without emit_runs) */
-    k_stream_classify<5, true, false, false><<<grid, NH_BLOCK_THREADS, smem, st>>>(db, b, sp);
+  /* kraken2's defaults (k 35, l 31, current reverse-complement) get the instantiation with the
+   * constants compiled in; anything else with a window of 5 takes the generic one */
+  const bool kl_default = db.k == 35 && db.l == 31 && db.revcom_version != 0;
+  if (b.dbg_pos_min != nullptr) /* nh_debug_minimizers (never with emit_runs) */
+    k_stream_classify<5, 0, true, false, false><<<grid, NH_BLOCK_THREADS, smem, st>>>(db, b, sp);
+  else if (kl_default && emit)
+    k_stream_classify<5, 1, false, false, true><<<grid, NH_BLOCK_THREADS, smem, st>>>(db, b, sp);
+  else if (kl_default)
+    k_stream_classify<5, 1, false, false, false><<<grid, NH_BLOCK_THREADS, smem, st>>>(db, b, sp);
   else if (db.revcom_version == 0 && emit)
-    k_stream_classify<5, false, true, true><<<grid, NH_BLOCK_THREADS, smem, st>>>(db, b, sp);
+    k_stream_classify<5, 0, false, true, true><<<grid, NH_BLOCK_THREADS, smem, st>>>(db, b, sp);
   else if (db.revcom_version == 0)
-    k_stream_classify<5, false, true, false><<<grid, NH_BLOCK_THREADS, smem, st>>>(db, b, sp);
+    k_stream_classify<5, 0, false, true, false><<<grid, NH_BLOCK_THREADS, smem, st>>>(db, b, sp);
   else if (emit)
-    k_stream_classify<5, false, false, true><<<grid, NH_BLOCK_THREADS, smem, st>>>(db, b, sp);
+    k_stream_classify<5, 0, false, false, true><<<grid, NH_BLOCK_THREADS, smem, st>>>(db, b, sp);
   else
-    k_stream_classify<5, false, false, false><<<grid, NH_BLOCK_THREADS, smem, st>>>(db, b, sp);
+    k_stream_classify<5, 0, false, false, false><<<grid, NH_BLOCK_THREADS, smem, st>>>(db, b, sp);
   return 1;
 }
 
@@ -1431,8 +1527,15 @@ int nh_launch_gather_runs(const NhDbParams &db, const NhBatchPtrs &b, uint32_t t
   return 1;
 }
 
-int nh_launch_random_gather(const uint32_t *cells, uint64_t n_sectors, uint64_t n_reads,
-                            uint64_t seed, uint32_t *sink, int sm_count, cudaStream_t st) {
-  k_random_gather<<<sm_count * 8, 256, 0, st>>>(cells, n_sectors, n_reads, seed, sink);
+int nh_launch_probe_pattern(const uint32_t *cells, uint64_t n_sectors, int lanes, uint32_t items_per_chain,
+                            uint32_t p_thresh, uint64_t seed, uint64_t sm_window_sectors,
+                            unsigned long long *counters, uint32_t *sink, int sm_count, cudaStream_t st) {
+  const int grid = sm_count * 8; /* 2048 threads per SM: as many chains in flight as the SM holds */
+  if (lanes == 4)
+    k_probe_pattern<4, 4><<<grid, 256, 0, st>>>(cells, n_sectors, items_per_chain, p_thresh, seed, sm_window_sectors, counters, sink);
+  else if (lanes == 2)
+    k_probe_pattern<2, 4><<<grid, 256, 0, st>>>(cells, n_sectors, items_per_chain, p_thresh, seed, sm_window_sectors, counters, sink);
+  else
+    k_probe_pattern<1, 4><<<grid, 256, 0, st>>>(cells, n_sectors, items_per_chain, p_thresh, seed, sm_window_sectors, counters, sink);
   return 1;
 }

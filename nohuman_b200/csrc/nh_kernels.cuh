@@ -93,6 +93,8 @@ struct NhCounters {
   uint32_t error;        /* nonzero: a unit exceeded even the big table */
   uint32_t n_deferred;   /* units k_score handles (not scored inside the fused kernel) */
   uint32_t next_group;   /* streaming kernel: next group of 32 tiles to hand out */
+  uint32_t n_sector_reads; /* streaming kernel: table sectors requested (lookups + chain continuations) */
+  uint32_t pad[3];
 };
 
 struct NhBatchPtrs {
@@ -151,8 +153,9 @@ int nh_launch_score(const NhDbParams &db, const NhBatchPtrs &b, const NhScorePar
 int nh_launch_gather_runs(const NhDbParams &db, const NhBatchPtrs &b, uint32_t tiles_upper,
                           uint32_t *run_ext, uint16_t *run_len, uint32_t *tile_run_off,
                           uint32_t *cursor, int sm_count, cudaStream_t st);
-int nh_launch_random_gather(const uint32_t *cells, uint64_t n_sectors, uint64_t n_reads,
-                            uint64_t seed, uint32_t *sink, int sm_count, cudaStream_t st);
+int nh_launch_probe_pattern(const uint32_t *cells, uint64_t n_sectors, int lanes, uint32_t items_per_chain,
+                            uint32_t p_thresh, uint64_t seed, uint64_t sm_window_sectors,
+                            unsigned long long *counters, uint32_t *sink, int sm_count, cudaStream_t st);
 cudaError_t nh_kernels_init(void);
 
 #endif

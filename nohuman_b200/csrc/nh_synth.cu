@@ -263,9 +263,10 @@ k_synth_reads(uint8_t *__restrict__ bases, const uint64_t *__restrict__ off, uin
       const uint64_t h2 = nh_fmix64(hu + 1);
       /* ~normal from 4 uniforms */
       float z = 0.f;
-      for (int i = 0; i < 4; i++) z += (float)((h2 >> (16 * i)) & 0xFFFFu) * (1.0f / 65536.0f);
-      z = (z - 2.0f) * 1.7320508f;
-      long long fl = (long long)(P.insert_mean + P.insert_sd * z);
+      /* explicit fused multiply-adds: oracle/k2_synth.c computes the same bits with fmaf() */
+      for (int i = 0; i < 4; i++) z = __fmaf_rn((float)((h2 >> (16 * i)) & 0xFFFFu), 1.0f / 65536.0f, z);
+      z = __fmul_rn(__fsub_rn(z, 2.0f), 1.7320508f);
+      long long fl = (long long)__fmaf_rn(P.insert_sd, z, P.insert_mean);
       const uint64_t other = s ^ 1ULL;
       const uint64_t len_other = off[other + 1] - off[other];
       const uint64_t lmax = len > len_other ? len : len_other;

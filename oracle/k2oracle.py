@@ -19,10 +19,9 @@ _LIB_PATH = os.path.join(_HERE, "libk2oracle.so")
 
 def build(force: bool = False) -> str:
     """Compile the oracle with the committed Makefile (gcc, seconds)."""
-    src = os.path.join(_HERE, "k2_oracle.c")
-    hdr = os.path.join(_HERE, "k2_oracle.h")
+    deps = [os.path.join(_HERE, f) for f in ("k2_oracle.c", "k2_synth.c", "k2_oracle.h", "Makefile")]
     stale = (not os.path.exists(_LIB_PATH)) or any(
-        os.path.getmtime(p) > os.path.getmtime(_LIB_PATH) for p in (src, hdr)
+        os.path.getmtime(p) > os.path.getmtime(_LIB_PATH) for p in deps
     )
     if force or stale:
         subprocess.check_call(["make", "-C", _HERE, "-s", "-B"])

@@ -197,3 +197,38 @@ class _DevPtr:
     def __init__(self, ptr, nbytes):
         self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3,
                                          "strides": None}
+
+
+def test_cpu_twin_of_the_generator_matches_the_gpu(sdb, odb):
+    """bench.py's reference arm builds its table and samples its reads with oracle/k2_synth.c instead of the
+    CUDA library: same genome, byte-identical reads, and a table that answers like the GPU-built one."""
+    import torch
+    from nohuman_b200 import synth
+    from oracle import k2synth
+    cap = int(sdb.db.info.capacity)
+    cdb, meta = k2synth.build_synthetic_db(cap, block_bases=1 << 14)
+    assert abs(meta["genome_bases"] - sdb.genome_bases) < 4096
+    assert abs(meta["hash_header"][1] - int(sdb.db.info.size)) < 64  # layout differs, occupancy does not
+    g_gpu = synth.synth_genome(0, sdb.genome_seed, 12345, 100_000)
+    g_cpu = k2synth.synth_genome(sdb.genome_seed, 12345, 100_000)
+    assert np.array_equal(g_gpu, g_cpu)
+    for paired, ins in ((True, 0.0), (False, 0.02)):
+        n = 6000
+        rng = np.random.default_rng(3)
+        lens = np.full(n, 150, np.int64) if paired else rng.integers(20, 3000, size=n)
+        off = np.zeros(n + 1, np.int64)
+        np.cumsum(lens, out=off[1:])
+        total = int(off[-1])
+        d_off = torch.from_numpy(off).cuda()
+        d_bases = torch.zeros(total + 64, dtype=torch.uint8, device="cuda")
+        kw = dict(seed=11, human_frac=0.5, sub_rate=0.01, ins_rate=ins, del_rate=ins, n_rate=0.05, paired=paired,
+                  insert_mean=350.0, insert_sd=50.0)
+        synth.synth_reads(0, d_bases.data_ptr(), d_off.data_ptr(), n, sdb.genome_seed, 2 * cap, **kw)
+        torch.cuda.synchronize()
+        gpu = d_bases[:total].cpu().numpy()
+        cpu = k2synth.synth_reads(off.astype(np.uint64), sdb.genome_seed, 2 * cap, **kw)
+        assert np.array_equal(gpu, cpu), (paired, int((gpu != cpu).sum()))
+        odb.confidence = cdb.confidence = 0.1
+        a = odb.classify_batch(gpu, off.astype(np.uint64), paired=paired)
+        b = cdb.classify_batch(cpu, off.astype(np.uint64), paired=paired)
+        assert (a["ext"] != b["ext"]).mean() < 1e-3  # only compacted-key collisions of absent keys can differ

@@ -56,3 +56,48 @@ def test_taxonomy_image_matches_oracle_builder(oracle, tmp_path):
     assert len(leaves) == 15 and all(l in internal for l in leaves)
     # the human lineage is there, so a report line for 9606 reads "S ... Homo sapiens"
     assert internal[9606] and tax.nodes[internal[9606]].parent_id == internal[9605]
+
+
+def test_cpu_twin_builds_a_valid_table(oracle):
+    """oracle/k2_synth.c (what `bench.py --impl reference` builds its table with): every minimizer the
+    oracle's own scanner finds in the synthetic genome is retrievable and carries the block's leaf or an
+    ancestor of it; the load factor lands on the target; a second build gives the same lookups."""
+    from oracle import k2synth
+    cap = (1 << 18) + 7
+    db, meta = k2synth.build_synthetic_db(cap, block_bases=1 << 13)
+    hdr = meta["hash_header"]
+    assert hdr[0] == cap and 0.69 < hdr[1] / cap < 0.72
+    cells = db.cells()
+    vmask = (1 << hdr[3]) - 1
+    assert int(((cells & vmask) != 0).sum()) == hdr[1]
+    g = k2synth.synth_genome(meta["genome_seed"], 0, 120_000)
+    assert set(np.unique(g).tolist()) <= set(b"ACGT")
+    mins, amb = oracle.scan_positions(db.opts, bytes(g))
+    assert not amb.any()
+    nodes, leaves = synth.human_pangenome_taxonomy()
+    leaf_int = [meta["internal"][x] for x in leaves]
+    block, tile = 1 << 13, 124
+    n_lca = 0
+    for p in range(0, len(mins), 29):
+        v = db.get(int(mins[p]))
+        assert v != 0, p
+        leaf = leaf_int[((p // tile * tile) // block) % len(leaf_int)]
+        assert oracle.lib().k2o_is_a_ancestor_of_b(C.byref(db.tax), v, leaf), (p, v, leaf)
+        n_lca += v != leaf
+    assert n_lca > 0
+    db2, meta2 = k2synth.build_synthetic_db(cap, block_bases=1 << 13, threads=1)
+    assert meta2["genome_bases"] == meta["genome_bases"] and meta2["hash_header"] == hdr
+    assert all(db2.get(int(m)) == db.get(int(m)) for m in mins[::101])
+
+
+def test_cpu_twin_reads_are_deterministic_and_half_human(oracle):
+    from oracle import k2synth
+    cap = (1 << 18) + 7
+    db, meta = k2synth.build_synthetic_db(cap, block_bases=1 << 13)
+    off = (np.arange(4001) * 150).astype(np.uint64)
+    a = k2synth.synth_reads(off, meta["genome_seed"], 2 * cap, seed=3, paired=True, threads=1)
+    b = k2synth.synth_reads(off, meta["genome_seed"], 2 * cap, seed=3, paired=True, threads=4)
+    assert np.array_equal(a, b) and set(np.unique(a).tolist()) <= set(b"ACGTN")
+    db.confidence = 0.5
+    r = db.classify_batch(a, off, paired=True)
+    assert 0.4 < (r["ext"] != 0).mean() < 0.6
