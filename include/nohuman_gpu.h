@@ -222,12 +222,16 @@ int nh_debug_last_batch(nh_session *s, uint32_t *out_call_internal, uint32_t *ou
 int nh_bench_random_gather(nh_db *db, uint64_t n_reads, int iters, double *out_gbs);
 /* The probe's own access pattern over the resident table, nothing else: every chain reads a random
  * sector and, with probability p_continue, the adjacent one once the first has arrived; `lanes`
- * (1, 2, 4) lanes share an item and read an aligned block of that many sectors in one instruction;
+ * (1, 2, 4) lanes share an item and read an aligned block of that many sectors in one instruction
+ * (lanes = 0: one sector per lane fetched the way k_stream_classify does it, by lane pairs with
+ * cp.async into shared memory; depth 1 or 2 rounds in flight per warp, no SM windows);
+ * every thread keeps `depth` (1, 2, 4) chains going and every SM runs `blocks_per_sm` (1..8) blocks
+ * of 256 threads, so callers can look for the best number of requests in flight;
  * sm_window_bytes > 0 confines each SM to its own window.  Returns the best of `iters` launches as
  * items (lookups) per second and table requests per second. */
-int nh_bench_probe_pattern(nh_db *db, int lanes, double p_continue, uint64_t sm_window_bytes,
-                           uint32_t items_per_chain, int iters, double *out_items_per_s,
-                           double *out_requests_per_s);
+int nh_bench_probe_pattern(nh_db *db, int lanes, int depth, int blocks_per_sm, double p_continue,
+                           uint64_t sm_window_bytes, uint32_t items_per_chain, int iters,
+                           double *out_items_per_s, double *out_requests_per_s);
 
 #ifdef __cplusplus
 }

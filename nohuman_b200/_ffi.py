@@ -110,8 +110,8 @@ SYMBOLS = {
     "nh_debug_probe": (_i32, [_vp, _vp, _u64, _vp]),
     "nh_debug_last_batch": (_i32, [_vp, _vp, _vp, _vp, _u64]),
     "nh_bench_random_gather": (_i32, [_vp, _u64, _i32, C.POINTER(C.c_double)]),
-    "nh_bench_probe_pattern": (_i32, [_vp, _i32, C.c_double, _u64, C.c_uint32, _i32, C.POINTER(C.c_double),
-                                      C.POINTER(C.c_double)]),
+    "nh_bench_probe_pattern": (_i32, [_vp, _i32, _i32, _i32, C.c_double, _u64, C.c_uint32, _i32,
+                                      C.POINTER(C.c_double), C.POINTER(C.c_double)]),
 }
 
 _lib = None

@@ -112,11 +112,12 @@ class Database:
         return out.value
 
     def probe_pattern(self, lanes: int = 1, p_continue: float = 0.41, sm_window_bytes: int = 0,
-                      items_per_chain: int = 64, iters: int = 3) -> tuple[float, float]:
+                      items_per_chain: int = 64, iters: int = 3, depth: int = 4,
+                      blocks_per_sm: int = 8) -> tuple[float, float]:
         """(lookups/s, table requests/s) of the probe's access pattern alone (nh_bench_probe_pattern)."""
         a, b = C.c_double(), C.c_double()
-        check(lib().nh_bench_probe_pattern(self._h, lanes, p_continue, sm_window_bytes, items_per_chain, iters,
-                                           C.byref(a), C.byref(b)))
+        check(lib().nh_bench_probe_pattern(self._h, lanes, depth, blocks_per_sm, p_continue, sm_window_bytes,
+                                           items_per_chain, iters, C.byref(a), C.byref(b)))
         return a.value, b.value
 
     def close(self) -> None:

@@ -911,11 +911,13 @@ extern "C" int nh_last_batch_runs(nh_session *s, uint64_t n_seqs, uint32_t *seq_
 }
 
 /* ------------------------------------------------------------------ */
-extern "C" int nh_bench_probe_pattern(nh_db *db, int lanes, double p_continue, uint64_t sm_window_bytes,
-                                      uint32_t items_per_chain, int iters, double *out_items_per_s,
-                                      double *out_requests_per_s) {
+extern "C" int nh_bench_probe_pattern(nh_db *db, int lanes, int depth, int blocks_per_sm, double p_continue,
+                                      uint64_t sm_window_bytes, uint32_t items_per_chain, int iters,
+                                      double *out_items_per_s, double *out_requests_per_s) {
   if (!db || !out_items_per_s || !out_requests_per_s || iters < 1 || items_per_chain < 1 ||
-      (lanes != 1 && lanes != 2 && lanes != 4) || !(p_continue >= 0.0 && p_continue < 1.0))
+      (lanes != 0 && lanes != 1 && lanes != 2 && lanes != 4) || (depth != 1 && depth != 2 && depth != 4) ||
+      (lanes == 0 && (depth == 4 || sm_window_bytes)) || blocks_per_sm < 1 ||
+      blocks_per_sm > 8 || !(p_continue >= 0.0 && p_continue < 1.0))
     return nh_set_error(NH_ERR_INVALID, "bad argument");
   CUDA_TRY(cudaSetDevice(db->info.device));
   const uint64_t n_sectors = db->info.capacity / 8;
@@ -935,8 +937,8 @@ extern "C" int nh_bench_probe_pattern(nh_db *db, int lanes, double p_continue, u
   for (int i = 0; i < iters + 1; i++) { /* first launch is warm-up */
     cudaMemsetAsync(d_cnt, 0, 16, st);
     cudaEventRecord(e0, st);
-    nh_launch_probe_pattern(db->d_cells, n_sectors, lanes, items_per_chain, p_thresh, 0x1234567ULL * (uint64_t)(i + 1),
-                            sm_window_bytes / 32, d_cnt, sink, db->sm_count, st);
+    nh_launch_probe_pattern(db->d_cells, n_sectors, lanes, depth, blocks_per_sm, items_per_chain, p_thresh,
+                            0x1234567ULL * (uint64_t)(i + 1), sm_window_bytes / 32, d_cnt, sink, db->sm_count, st);
     cudaEventRecord(e1, st);
     unsigned long long h[2] = {0, 0};
     cudaMemcpyAsync(h, d_cnt, 16, cudaMemcpyDeviceToHost, st);
@@ -966,7 +968,7 @@ extern "C" int nh_bench_random_gather(nh_db *db, uint64_t n_reads, int iters, do
   uint64_t per = n_reads / chains;
   if (per < 1) per = 1;
   double items = 0, req = 0;
-  int rc = nh_bench_probe_pattern(db, 1, 0.0, 0, (uint32_t)per, iters, &items, &req);
+  int rc = nh_bench_probe_pattern(db, 1, 4, 8, 0.0, 0, (uint32_t)per, iters, &items, &req);
   if (rc) return rc;
   *out_gbs = req * 32.0 / 1e9;
   return NH_OK;

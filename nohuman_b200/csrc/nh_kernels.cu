@@ -1337,6 +1337,75 @@ k_gather_runs(const NhDbParams db, const NhBatchPtrs b, uint32_t *__restrict__ r
  * No hashing of k-mers, no scan, no scoring: whatever this reaches is an upper
  * bound for any kernel that makes the same table requests.
  */
+/* the streaming kernel's own fetch: lane pairs copy the two halves of a sector with cp.async */
+__device__ __forceinline__ void fetch_sector_async(const uint32_t *cells, uint64_t sector, uint32_t smem_slot0, uint32_t lane) {
+  const uint32_t half = lane & 1u, src_lane = lane >> 1;
+  const uint64_t u0 = __shfl_sync(FULL_MASK, sector, src_lane);
+  const uint64_t u1 = __shfl_sync(FULL_MASK, sector, 16u + src_lane);
+  const uint32_t dst = smem_slot0 + src_lane * 32u + half * 16u;
+  cp_async16_l2_64(dst, cells + u0 * 8ULL + half * 4u);
+  cp_async16_l2_64(dst + 512u, cells + u1 * 8ULL + half * 4u);
+}
+
+/* DEPTH rounds in flight per warp, every round one sector per lane through cp.async + commit/wait groups */
+template <int DEPTH>
+__global__ void __launch_bounds__(256)
+k_probe_pattern_async(const uint32_t *__restrict__ cells, uint64_t n_sectors, uint32_t items_per_chain,
+                      uint32_t p_thresh, uint64_t seed, unsigned long long *__restrict__ counters,
+                      uint32_t *__restrict__ sink) {
+  __shared__ __align__(16) uint32_t s_sect[8][DEPTH][32 * 8];
+  const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+  const uint64_t chain0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * DEPTH;
+  uint64_t blk[DEPTH];
+  uint32_t left[DEPTH], cont[DEPTH];
+  uint32_t acc = 0;
+  unsigned long long items = 0, requests = 0;
+#pragma unroll
+  for (int d = 0; d < DEPTH; d++) {
+    blk[d] = __umul64hi(nh_fmix64(seed + (chain0 + d) * 0x9E3779B97F4A7C15ULL), n_sectors);
+    left[d] = items_per_chain;
+    cont[d] = 0;
+    fetch_sector_async(cells, blk[d], smem_addr(&s_sect[warp][d][0]), lane);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  for (uint32_t it = 1; it <= 2u * items_per_chain + 2u; it++) { /* warp-uniform trip count: lanes that are done idle along */
+#pragma unroll
+    for (int d = 0; d < DEPTH; d++) {
+      asm volatile("cp.async.wait_group %0;" ::"n"(DEPTH - 1) : "memory");
+      __syncwarp();
+      const uint4 lo = *reinterpret_cast<const uint4 *>(&s_sect[warp][d][lane * 8u]);
+      const uint4 hi = *reinterpret_cast<const uint4 *>(&s_sect[warp][d][lane * 8u + 4u]);
+      const uint32_t x = lo.x ^ lo.y ^ lo.z ^ lo.w ^ hi.x ^ hi.y ^ hi.z ^ hi.w;
+      __syncwarp();
+      if (left[d] != 0u) {
+        acc ^= x;
+        requests++;
+        const uint64_t h = nh_fmix64(seed ^ ((chain0 + d) << 20) ^ it ^ (uint64_t)(x & 1u) << 63);
+        if (!cont[d] && (uint32_t)h < p_thresh) {
+          cont[d] = 1;
+          blk[d] = blk[d] + 1 < n_sectors ? blk[d] + 1 : 0;
+        } else {
+          cont[d] = 0;
+          items++;
+          left[d]--;
+          blk[d] = __umul64hi(h, n_sectors);
+        }
+      }
+      fetch_sector_async(cells, blk[d], smem_addr(&s_sect[warp][d][0]), lane);
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    if (!__any_sync(FULL_MASK, left[0] != 0u || left[DEPTH - 1] != 0u)) break;
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  if (acc == 0x9E3779B9u) sink[0] = acc;
+  items = __reduce_add_sync(FULL_MASK, (uint32_t)items);
+  requests = __reduce_add_sync(FULL_MASK, (uint32_t)requests);
+  if (lane == 0) {
+    atomicAdd(&counters[0], items);
+    atomicAdd(&counters[1], requests);
+  }
+}
+
 template <int G, int DEPTH>
 __global__ void __launch_bounds__(256)
 k_probe_pattern(const uint32_t *__restrict__ cells, uint64_t n_sectors, uint32_t items_per_chain,
@@ -1527,15 +1596,27 @@ int nh_launch_gather_runs(const NhDbParams &db, const NhBatchPtrs &b, uint32_t t
   return 1;
 }
 
-int nh_launch_probe_pattern(const uint32_t *cells, uint64_t n_sectors, int lanes, uint32_t items_per_chain,
-                            uint32_t p_thresh, uint64_t seed, uint64_t sm_window_sectors,
+int nh_launch_probe_pattern(const uint32_t *cells, uint64_t n_sectors, int lanes, int depth, int blocks_per_sm,
+                            uint32_t items_per_chain, uint32_t p_thresh, uint64_t seed, uint64_t sm_window_sectors,
                             unsigned long long *counters, uint32_t *sink, int sm_count, cudaStream_t st) {
-  const int grid = sm_count * 8; /* 2048 threads per SM: as many chains in flight as the SM holds */
-  if (lanes == 4)
-    k_probe_pattern<4, 4><<<grid, 256, 0, st>>>(cells, n_sectors, items_per_chain, p_thresh, seed, sm_window_sectors, counters, sink);
-  else if (lanes == 2)
-    k_probe_pattern<2, 4><<<grid, 256, 0, st>>>(cells, n_sectors, items_per_chain, p_thresh, seed, sm_window_sectors, counters, sink);
-  else
-    k_probe_pattern<1, 4><<<grid, 256, 0, st>>>(cells, n_sectors, items_per_chain, p_thresh, seed, sm_window_sectors, counters, sink);
+  const int grid = sm_count * blocks_per_sm; /* 256 threads per block: 1..8 blocks per SM */
+  if (lanes == 0) { /* the streaming kernel's fetch (cp.async, lane pairs) */
+    if (depth == 1)
+      k_probe_pattern_async<1><<<grid, 256, 0, st>>>(cells, n_sectors, items_per_chain, p_thresh, seed, counters, sink);
+    else
+      k_probe_pattern_async<2><<<grid, 256, 0, st>>>(cells, n_sectors, items_per_chain, p_thresh, seed, counters, sink);
+    return 1;
+  }
+#define NH_PP(G, D)                                                                                                  \
+  k_probe_pattern<G, D><<<grid, 256, 0, st>>>(cells, n_sectors, items_per_chain, p_thresh, seed, sm_window_sectors, \
+                                              counters, sink)
+  if (lanes == 4) {
+    if (depth == 1) NH_PP(4, 1); else if (depth == 2) NH_PP(4, 2); else NH_PP(4, 4);
+  } else if (lanes == 2) {
+    if (depth == 1) NH_PP(2, 1); else if (depth == 2) NH_PP(2, 2); else NH_PP(2, 4);
+  } else {
+    if (depth == 1) NH_PP(1, 1); else if (depth == 2) NH_PP(1, 2); else NH_PP(1, 4);
+  }
+#undef NH_PP
   return 1;
 }

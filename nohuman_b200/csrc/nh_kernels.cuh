@@ -153,8 +153,8 @@ int nh_launch_score(const NhDbParams &db, const NhBatchPtrs &b, const NhScorePar
 int nh_launch_gather_runs(const NhDbParams &db, const NhBatchPtrs &b, uint32_t tiles_upper,
                           uint32_t *run_ext, uint16_t *run_len, uint32_t *tile_run_off,
                           uint32_t *cursor, int sm_count, cudaStream_t st);
-int nh_launch_probe_pattern(const uint32_t *cells, uint64_t n_sectors, int lanes, uint32_t items_per_chain,
-                            uint32_t p_thresh, uint64_t seed, uint64_t sm_window_sectors,
+int nh_launch_probe_pattern(const uint32_t *cells, uint64_t n_sectors, int lanes, int depth, int blocks_per_sm,
+                            uint32_t items_per_chain, uint32_t p_thresh, uint64_t seed, uint64_t sm_window_sectors,
                             unsigned long long *counters, uint32_t *sink, int sm_count, cudaStream_t st);
 cudaError_t nh_kernels_init(void);
 

@@ -232,3 +232,14 @@ def test_cpu_twin_of_the_generator_matches_the_gpu(sdb, odb):
         a = odb.classify_batch(gpu, off.astype(np.uint64), paired=paired)
         b = cdb.classify_batch(cpu, off.astype(np.uint64), paired=paired)
         assert (a["ext"] != b["ext"]).mean() < 1e-3  # only compacted-key collisions of absent keys can differ
+
+
+def test_probe_pattern_microbenchmark_counts(big_sdb):
+    """The roofline helper (nh_bench_probe_pattern): requests = items x (1 + spill rate) for every fetch
+    flavour, and more requests in flight are never slower by an order of magnitude (sanity, not a benchmark)."""
+    for lanes, depth in ((1, 1), (1, 4), (2, 2), (4, 1), (0, 1), (0, 2)):
+        items, req = big_sdb.db.probe_pattern(lanes=lanes, p_continue=0.4, items_per_chain=64, iters=1, depth=depth,
+                                              blocks_per_sm=4)
+        assert items > 1e9 and 1.3 < req / items < 1.5, (lanes, depth, items, req)
+    items0, req0 = big_sdb.db.probe_pattern(lanes=1, p_continue=0.0, items_per_chain=64, iters=1)
+    assert abs(req0 / items0 - 1.0) < 1e-6
