@@ -4,8 +4,10 @@
  * the path this repository rebuilds: --db / NOHUMAN_DB / --db-version, --conf,
  * -t, one or two inputs, --out1/--out2, -F, -H.  The external kraken2 process
  * (src/main.rs:170-270) and the compression pass after it (src/main.rs:340-368)
- * are one call to nh_run_files().  Not reproduced: --download and
- * --list-db-versions (network only).
+ * are one call to nh_run_files().  --list-db-versions reads the manifest the way
+ * download_config does when a local config.toml exists (src/download.rs:146-168,
+ * config.toml:1-19); its network half and --download are not reproduced
+ * (SURVEY.md §2 row 10).
  *
  * The same binary installed under the name `kraken2` accepts the argv nohuman
  * builds (src/main.rs:215-267) and prints the three stderr lines
@@ -180,6 +182,56 @@ static bool valid_date(const std::string &s) {
   char tail;
   return sscanf(s.c_str(), "%4d-%2d-%2d%c", &y, &m, &d, &tail) == 3 && m >= 1 && m <= 12 && d >= 1 && d <= 31;
 }
+/* ---- database manifest (config.toml; src/download.rs:54-98,146-176) ---- */
+struct Release {
+  std::string version, url, md5, added;
+};
+struct Manifest {
+  std::string default_version;
+  std::vector<Release> databases;
+};
+/* The subset of TOML the manifest uses: `key = "value"` lines and `[[databases]]` table headers.
+ * Returns an error text (empty on success); like the reference every `added` must be a date. */
+static std::string read_manifest(const std::string &path, Manifest &out) {
+  FILE *f = fopen(path.c_str(), "r");
+  if (!f) return "Failed to download database config"; /* DownloadError::ConfigDownloadFailed: no local file, no network */
+  char line[1024];
+  Release *cur = nullptr;
+  bool ok = true;
+  while (fgets(line, sizeof line, f)) {
+    char *p = line;
+    while (*p == ' ' || *p == '\t') p++;
+    if (*p == '#' || *p == '\n' || *p == '\r' || !*p) continue;
+    if (!strncmp(p, "[[databases]]", 13)) {
+      out.databases.emplace_back();
+      cur = &out.databases.back();
+      continue;
+    }
+    if (*p == '[') { /* some other table: not ours */
+      cur = nullptr;
+      continue;
+    }
+    char key[64], val[512];
+    if (sscanf(p, "%63[A-Za-z0-9_-] = \"%511[^\"]\"", key, val) != 2) {
+      ok = false;
+      continue;
+    }
+    if (!cur) {
+      if (!strcmp(key, "default_version")) out.default_version = val;
+    } else if (!strcmp(key, "version")) cur->version = val;
+    else if (!strcmp(key, "url")) cur->url = val;
+    else if (!strcmp(key, "md5")) cur->md5 = val;
+    else if (!strcmp(key, "added")) cur->added = val;
+  }
+  fclose(f);
+  for (auto &r : out.databases)
+    if (r.version.empty() || r.url.empty() || r.md5.empty() || r.added.empty()) ok = false;
+  if (!ok) return "Failed to parse database config";
+  for (auto &r : out.databases)
+    if (!valid_date(r.added)) return "Invalid date '" + r.added + "' in database manifest";
+  return "";
+}
+
 static std::vector<Installed> installed_databases(const std::string &root) {
   std::vector<Installed> v;
   if (DIR *d = opendir(root.c_str())) {
@@ -394,10 +446,23 @@ int main(int argc, char **argv) {
     const char *home = getenv("HOME");
     db = path_join(path_join(home ? home : "", ".nohuman"), "db");
   }
-  if (list || download)
-    return fail("%s needs network access to the database manifest, which this build does not include; "
-                "install a database directory (hash.k2d, opts.k2d, taxo.k2d) and pass it with --db",
-                list ? "--list-db-versions" : "--download");
+  if (list) {
+    /* src/main.rs:123-147 over download_config (src/download.rs:146-168): ./config.toml first; the
+     * reference would fetch CONFIG_URL next, which this build does not do */
+    Manifest m;
+    const std::string err = read_manifest("config.toml", m);
+    if (!err.empty())
+      return fail("Failed to download database manifest: %s%s", err.c_str(),
+                  exists("config.toml") ? "" : " (no config.toml in the working directory; this build does not fetch it from the network)");
+    printf("Available databases:\n");
+    for (auto &r : m.databases)
+      printf("- %s%s (added %s) -> %s\n", r.version.c_str(), r.version == m.default_version ? " (default)" : "",
+             r.added.c_str(), r.url.c_str());
+    return 0;
+  }
+  if (download)
+    return fail("--download needs network access, which this build does not include; "
+                "install a database directory (hash.k2d, opts.k2d, taxo.k2d) and pass it with --db");
   if (!plan && nh_device_count() < 1) {
     logmsg("ERROR", "The following dependencies are missing:");
     logmsg("ERROR", "a CUDA device (libnohuman_gpu has no CPU path)");

@@ -148,7 +148,36 @@ def test_database_resolution(tmp_path):
     assert kv["version"] == "legacy" and kv["db"] == legacy
 
 
+def test_list_db_versions_reads_the_local_manifest(tmp_path):
+    """src/main.rs:123-147 over download_config (src/download.rs:146-168): a config.toml in the working
+    directory is used before any network access; the listing format is the reference's.  The manifest
+    below is the reference's own config.toml (config.toml:1-19)."""
+    (tmp_path / "config.toml").write_text(
+        'default_version = "HPRC.r2"\n\n[[databases]]\nversion = "HPRC.r2"\n'
+        'url = "https://ndownloader.figshare.com/files/59658306"\nmd5 = "bda8fb2ffb1a0b4cbeb880cbc4d79fc6"\nadded = "2025-11-19"\n\n'
+        '[[databases]]\nversion = "HPRC.r1"\nurl = "https://zenodo.org/records/17626846/files/k2_HPRC_release1_20251110.tar.gz"\n'
+        'md5 = "1cdf55d3739729fce4012519cc4706f1"\nadded = "2025-11-17"\n\n'
+        '[[databases]]\nversion = "HPRC.r1.masked"\nurl = "https://zenodo.org/records/8339732/files/k2_HPRC_20230810.tar.gz"\n'
+        'md5 = "87275d884181cfb6b46fdb883195dacb"\nadded = "2023-08-10"\n')
+    r = subprocess.run([CLI, "--list-db-versions"], capture_output=True, text=True, cwd=tmp_path)
+    assert r.returncode == 0, r.stderr
+    assert r.stdout.splitlines() == [
+        "Available databases:",
+        "- HPRC.r2 (default) (added 2025-11-19) -> https://ndownloader.figshare.com/files/59658306",
+        "- HPRC.r1 (added 2025-11-17) -> https://zenodo.org/records/17626846/files/k2_HPRC_release1_20251110.tar.gz",
+        "- HPRC.r1.masked (added 2023-08-10) -> https://zenodo.org/records/8339732/files/k2_HPRC_20230810.tar.gz",
+    ]
+    # a release without a date, or with a malformed one, is refused like parse_added_date does (src/download.rs:290-292)
+    bad = tmp_path / "bad"
+    bad.mkdir()
+    (bad / "config.toml").write_text('[[databases]]\nversion = "x"\nurl = "u"\nmd5 = "m"\nadded = "yesterday"\n')
+    r = subprocess.run([CLI, "--list-db-versions"], capture_output=True, text=True, cwd=bad)
+    assert r.returncode != 0 and "Failed to download database manifest" in r.stderr
+
+
 def test_network_only_flags_say_so(tmp_path):
-    for flag in ("--download", "--list-db-versions"):
-        r = subprocess.run([CLI, flag], capture_output=True, text=True)
-        assert r.returncode != 0 and "network" in r.stderr
+    r = subprocess.run([CLI, "--download"], capture_output=True, text=True, cwd=tmp_path)
+    assert r.returncode != 0 and "network" in r.stderr
+    # no local manifest: the reference would fetch it; this build says that it does not
+    r = subprocess.run([CLI, "--list-db-versions"], capture_output=True, text=True, cwd=tmp_path)
+    assert r.returncode != 0 and "network" in r.stderr
