@@ -63,7 +63,7 @@ typedef struct {
   uint64_t capacity, size, key_bits, value_bits;
   uint64_t node_count;
   int32_t device;
-  int32_t reserved;
+  int32_t replicated_by; /* 0: read from disk / memory, 1: NCCL broadcast, 2: peer-copy tree (nh_db_open_multi) */
 } nh_db_info_t;
 
 typedef struct {
@@ -125,6 +125,13 @@ int nh_db_open(const char *db_dir, int device, nh_db **out);
 int nh_db_open_memory(const void *opts, size_t opts_len, const void *taxo, size_t taxo_len,
                       const uint64_t hash_header[4], const uint32_t *cells, int cells_on_device,
                       int device, nh_db **out);
+/* The boundary SURVEY.md §8(b) promised: ONE read of <db_dir> from disk, then the table is
+ * replicated onto every listed device — by an NCCL broadcast over NVLink / NVSwitch (libnccl.so.2
+ * bound at run time), or by a binomial tree of peer copies when NCCL is not available
+ * (NH_DB_REPLICATE=p2p forces the tree).  out[n_devices] receives one independent nh_db per
+ * device, out[0] on device_ids[0]; nh_db_info().replicated_by says how each one arrived.
+ * This is what replaces kraken2 loading the database once per process (reference src/main.rs:270). */
+int nh_db_open_multi(const char *db_dir, const int *device_ids, int n_devices, nh_db **out);
 /* Replicate an open database onto another device of this process (peer copy,
  * NVLink when the devices are connected); the clone is independent of `src`. */
 int nh_db_clone(const nh_db *src, int device, nh_db **out);

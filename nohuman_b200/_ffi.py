@@ -38,7 +38,7 @@ class DbInfo(C.Structure):
         ("dna_db", C.c_int32), ("revcom_version", C.c_int32),
         ("capacity", C.c_uint64), ("size", C.c_uint64), ("key_bits", C.c_uint64),
         ("value_bits", C.c_uint64), ("node_count", C.c_uint64),
-        ("device", C.c_int32), ("reserved", C.c_int32),
+        ("device", C.c_int32), ("replicated_by", C.c_int32),
     ]
 
 
@@ -91,6 +91,7 @@ SYMBOLS = {
     "nh_db_open_memory": (_i32, [_vp, C.c_size_t, _vp, C.c_size_t, C.POINTER(_u64), _vp, _i32, _i32,
                                  C.POINTER(_vp)]),
     "nh_db_info": (_i32, [_vp, C.POINTER(DbInfo)]),
+    "nh_db_open_multi": (_i32, [C.c_char_p, C.POINTER(_i32), _i32, C.POINTER(_vp)]),
     "nh_db_clone": (_i32, [_vp, _i32, C.POINTER(_vp)]),
     "nh_db_device_cells": (_vp, [_vp]),
     "nh_db_close": (None, [_vp]),

@@ -76,6 +76,14 @@ class Database:
         return cls(h.value)
 
     @classmethod
+    def open_multi(cls, db_dir: str, devices: list[int]) -> list["Database"]:
+        """One disk read, one replica per device (NCCL broadcast, or a peer-copy tree): nh_db_open_multi."""
+        ids = (C.c_int * len(devices))(*devices)
+        hs = (C.c_void_p * len(devices))()
+        check(lib().nh_db_open_multi(str(db_dir).encode(), ids, len(devices), hs))
+        return [cls(h) for h in hs]
+
+    @classmethod
     def from_memory(cls, opts: bytes, taxo: bytes, hash_header, cells, device: int = 0,
                     cells_on_device: bool = False) -> "Database":
         """cells: numpy uint32 array (host) or an int device pointer."""

@@ -6,6 +6,7 @@
  * nh_kernels.cu.  No CPU classification path exists here.
  */
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 #include <stdarg.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -435,6 +436,144 @@ extern "C" int nh_db_clone(const nh_db *src, int device, nh_db **out) {
     return rc;
   }
   *out = db;
+  return NH_OK;
+}
+
+/* ------------------------------------------------------------------ */
+/* one disk read, N replicas: NCCL broadcast over NVLink / NVSwitch        */
+
+/* NCCL is bound at run time (libnccl.so.2 is in the image; a process that already loaded torch's
+ * copy gets that one): no link-time dependency, and a box without it still gets the peer-copy tree */
+namespace {
+typedef struct ncclComm *nccl_comm_t;
+struct Nccl {
+  void *h = nullptr;
+  int (*CommInitAll)(nccl_comm_t *, int, const int *) = nullptr;
+  int (*CommDestroy)(nccl_comm_t) = nullptr;
+  int (*GroupStart)(void) = nullptr;
+  int (*GroupEnd)(void) = nullptr;
+  int (*Broadcast)(const void *, void *, size_t, int /* ncclDataType_t */, int, nccl_comm_t, cudaStream_t) = nullptr;
+  const char *(*GetErrorString)(int) = nullptr;
+  bool load() {
+    const char *off = getenv("NH_DB_REPLICATE");
+    if (off && !strcmp(off, "p2p")) return false;
+    h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
+    if (!h) return false;
+    CommInitAll = (decltype(CommInitAll))dlsym(h, "ncclCommInitAll");
+    CommDestroy = (decltype(CommDestroy))dlsym(h, "ncclCommDestroy");
+    GroupStart = (decltype(GroupStart))dlsym(h, "ncclGroupStart");
+    GroupEnd = (decltype(GroupEnd))dlsym(h, "ncclGroupEnd");
+    Broadcast = (decltype(Broadcast))dlsym(h, "ncclBroadcast");
+    GetErrorString = (decltype(GetErrorString))dlsym(h, "ncclGetErrorString");
+    return CommInitAll && CommDestroy && GroupStart && GroupEnd && Broadcast && GetErrorString;
+  }
+};
+}  // namespace
+
+/* an empty replica of `src` on `device`: same metadata, table allocated but not filled */
+static int db_alloc_replica(const nh_db *src, int device, nh_db **out) {
+  int rc = select_device(device);
+  if (rc) return rc;
+  nh_db *db = new nh_db();
+  db->info = src->info;
+  db->info.device = device;
+  db->h_parent = src->h_parent;
+  db->h_ext = src->h_ext;
+  db->h_ext64 = src->h_ext64;
+  db->h_name = src->h_name;
+  db->h_rank = src->h_rank;
+  const size_t bytes = ((src->info.capacity + 31) / 32) * 128;
+  cudaError_t e = cudaMalloc(&db->d_cells, bytes);
+  if (e != cudaSuccess) {
+    delete db;
+    return nh_set_error(NH_ERR_NOMEM, "cudaMalloc(%zu) for the hash table on device %d failed: %s", bytes, device,
+                        cudaGetErrorString(e));
+  }
+  db->owns_cells = true;
+  *out = db;
+  return NH_OK;
+}
+
+extern "C" int nh_db_open_multi(const char *db_dir, const int *device_ids, int n_devices, nh_db **out) {
+  if (!db_dir || !device_ids || !out || n_devices < 1) return nh_set_error(NH_ERR_INVALID, "bad argument");
+  for (int i = 0; i < n_devices; i++)
+    for (int j = 0; j < i; j++)
+      if (device_ids[i] == device_ids[j]) return nh_set_error(NH_ERR_INVALID, "device %d listed twice", device_ids[i]);
+  for (int i = 0; i < n_devices; i++) out[i] = nullptr;
+  int rc = nh_db_open(db_dir, device_ids[0], &out[0]); /* the only disk read */
+  if (rc || n_devices == 1) return rc;
+  auto cleanup = [&](int code) {
+    for (int i = 0; i < n_devices; i++)
+      if (out[i]) nh_db_close(out[i]), out[i] = nullptr;
+    return code;
+  };
+  for (int i = 1; i < n_devices; i++)
+    if ((rc = db_alloc_replica(out[0], device_ids[i], &out[i])) != NH_OK) return cleanup(rc);
+  const size_t bytes = ((out[0]->info.capacity + 31) / 32) * 128;
+  std::vector<cudaStream_t> streams((size_t)n_devices, nullptr);
+  for (int i = 0; i < n_devices; i++) {
+    cudaSetDevice(device_ids[i]);
+    cudaStreamCreateWithFlags(&streams[(size_t)i], cudaStreamNonBlocking);
+  }
+  int how = 0;
+  Nccl nccl;
+  if (nccl.load()) {
+    std::vector<nccl_comm_t> comms((size_t)n_devices, nullptr);
+    int nr = nccl.CommInitAll(comms.data(), n_devices, device_ids);
+    if (nr == 0) {
+      nccl.GroupStart();
+      for (int i = 0; i < n_devices && nr == 0; i++) {
+        cudaSetDevice(device_ids[i]);
+        nr = nccl.Broadcast(out[0]->d_cells, out[i]->d_cells, bytes, 1 /* ncclUint8 */, 0, comms[(size_t)i], streams[(size_t)i]);
+      }
+      const int ge = nccl.GroupEnd();
+      if (nr == 0) nr = ge;
+      for (int i = 0; i < n_devices; i++) {
+        cudaSetDevice(device_ids[i]);
+        if (cudaStreamSynchronize(streams[(size_t)i]) != cudaSuccess && nr == 0) nr = -1;
+      }
+      for (auto c : comms)
+        if (c) nccl.CommDestroy(c);
+    }
+    if (nr == 0) how = 1;
+    else cudaGetLastError(); /* fall through to the peer copies */
+  }
+  if (!how) {
+    /* binomial tree of peer copies: round r doubles the number of replicas (3 rounds for 8 GPUs),
+     * every copy of a round on its own stream so they run side by side over NVSwitch */
+    cudaError_t e = cudaSuccess;
+    for (int have = 1; have < n_devices && e == cudaSuccess; have *= 2) {
+      for (int i = 0; i < have && have + i < n_devices; i++) {
+        const int src = i, dst = have + i;
+        int can = 0;
+        cudaSetDevice(device_ids[dst]);
+        if (cudaDeviceCanAccessPeer(&can, device_ids[dst], device_ids[src]) == cudaSuccess && can)
+          if (cudaDeviceEnablePeerAccess(device_ids[src], 0) != cudaSuccess) cudaGetLastError();
+        e = cudaMemcpyPeerAsync(out[dst]->d_cells, device_ids[dst], out[src]->d_cells, device_ids[src], bytes, streams[(size_t)dst]);
+        if (e != cudaSuccess) break;
+      }
+      for (int i = 0; i < have && have + i < n_devices; i++) {
+        cudaSetDevice(device_ids[have + i]);
+        const cudaError_t se = cudaStreamSynchronize(streams[(size_t)(have + i)]);
+        if (e == cudaSuccess) e = se;
+      }
+    }
+    if (e != cudaSuccess) {
+      for (auto st : streams) cudaStreamDestroy(st);
+      return cleanup(nh_set_error(NH_ERR_CUDA, "replicating the hash table failed: %s", cudaGetErrorString(e)));
+    }
+    how = 2;
+  }
+  for (int i = 0; i < n_devices; i++) {
+    cudaSetDevice(device_ids[i]);
+    cudaStreamDestroy(streams[(size_t)i]);
+  }
+  const uint64_t hdr[4] = {out[0]->info.capacity, out[0]->info.size, out[0]->info.key_bits, out[0]->info.value_bits};
+  for (int i = 1; i < n_devices; i++) {
+    cudaSetDevice(device_ids[i]);
+    if ((rc = finish_db(out[i], hdr)) != NH_OK) return cleanup(rc);
+    out[i]->info.replicated_by = how;
+  }
   return NH_OK;
 }
 

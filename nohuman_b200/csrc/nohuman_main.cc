@@ -522,8 +522,17 @@ int main(int argc, char **argv) {
            db_path.c_str(), version.c_str(), fmt, out1.c_str(), out2.c_str(), (int)paired, (int)human, conf, threads);
     return 0;
   }
-  nh_db *dbh = nullptr;
-  if (nh_db_open(db_path.c_str(), gpu, &dbh)) return fail("%s", nh_last_error());
+  /* more GPUs: the table is read from disk once and broadcast (NCCL over NVLink, else peer copies);
+   * nothing is exchanged between the GPUs afterwards */
+  if (gpus < 0) gpus = nh_device_count() - gpu;
+  if (gpus < 1 || gpu + gpus > nh_device_count()) return fail("--gpus %d from device %d: only %d device(s) visible", gpus, gpu, nh_device_count());
+  std::vector<int> devs;
+  for (int g = 0; g < gpus; g++) devs.push_back(gpu + g);
+  std::vector<nh_db *> replicas((size_t)gpus, nullptr);
+  struct timespec t_load0, t_load1;
+  clock_gettime(CLOCK_MONOTONIC, &t_load0);
+  if (nh_db_open_multi(db_path.c_str(), devs.data(), gpus, replicas.data())) return fail("%s", nh_last_error());
+  clock_gettime(CLOCK_MONOTONIC, &t_load1);
   nh_params_t p;
   memset(&p, 0, sizeof p);
   p.confidence = conf;
@@ -531,23 +540,23 @@ int main(int argc, char **argv) {
   p.paired = paired;
   p.keep_human = human;
   p.threads = (int)threads;
-  p.max_batch_bases = 1u << 20; /* parameter carrier only: nh_run_files sizes its own sessions per chunk */
+  p.max_batch_bases = 1u << 20; /* parameter carrier only: nh_run_files sizes its own sessions */
   p.max_batch_seqs = 1u << 12;
-  nh_session *sess = nullptr;
-  if (nh_session_create(dbh, &p, &sess)) return fail("%s", nh_last_error());
-  /* more GPUs: replicate the table once (peer copies), no exchange afterwards */
-  if (gpus < 0) gpus = nh_device_count() - gpu;
-  if (gpus < 1 || gpu + gpus > nh_device_count()) return fail("--gpus %d from device %d: only %d device(s) visible", gpus, gpu, nh_device_count());
-  std::vector<nh_db *> replicas{dbh};
-  std::vector<nh_session *> sessions{sess};
-  for (int g = 1; g < gpus; g++) {
-    nh_db *r = nullptr;
+  std::vector<nh_session *> sessions;
+  for (int g = 0; g < gpus; g++) {
     nh_session *rs = nullptr;
-    if (nh_db_clone(dbh, gpu + g, &r) || nh_session_create(r, &p, &rs)) return fail("%s", nh_last_error());
-    replicas.push_back(r);
+    if (nh_session_create(replicas[(size_t)g], &p, &rs)) return fail("%s", nh_last_error());
     sessions.push_back(rs);
   }
-  if (gpus > 1) logmsg("INFO", "Database replicated on %d GPUs", gpus);
+  {
+    nh_db_info_t di;
+    memset(&di, 0, sizeof di);
+    if (gpus > 1) nh_db_info(replicas[1], &di);
+    const double load_s = (double)(t_load1.tv_sec - t_load0.tv_sec) + 1e-9 * (double)(t_load1.tv_nsec - t_load0.tv_nsec);
+    if (gpus > 1)
+      logmsg("INFO", "Database replicated on %d GPUs (%s)", gpus, di.replicated_by == 1 ? "NCCL broadcast" : "peer copies");
+    logmsg("DEBUG", "database load: %.3f s on %d GPU(s)", load_s, gpus);
+  }
   logmsg("INFO", human ? "Keeping human reads..." : "Removing human reads...");
   nh_files_t f;
   memset(&f, 0, sizeof f);
