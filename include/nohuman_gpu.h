@@ -103,6 +103,16 @@ typedef struct {
   uint64_t unclassified; /* "N sequences unclassified" */
   uint64_t bases;
   double seconds;
+  /* where the host threads spent their time: busy seconds per stage, summed over the stage's
+   * threads (waiting for another stage is not counted); seconds above is the wall clock */
+  double busy_inflate_s;   /* decompressing the inputs (1 thread per plain-gzip / bzip2 file, a pool for blocked gzip) */
+  double busy_parse_s;     /* FASTQ / FASTA parsing (1 thread per input file) */
+  double busy_stage_s;     /* interleaving mates into the pinned transfer buffers (2 threads per GPU) */
+  double busy_classify_s;  /* inside nh_classify_batch: H2D, kernels, D2H (same threads) */
+  double busy_serialise_s; /* re-serialising kept records, per-read output lines (same threads) */
+  double busy_compress_s;  /* output compression (-t threads) */
+  double busy_write_s;     /* ordered writes to the output files (1 thread) */
+  int32_t threads_inflate, threads_compress;
 } nh_run_stats_t;
 
 /* ------------------------------------------------------------------ */

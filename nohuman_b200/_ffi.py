@@ -70,6 +70,9 @@ class RunStats(C.Structure):
     _fields_ = [
         ("total", C.c_uint64), ("classified", C.c_uint64), ("unclassified", C.c_uint64),
         ("bases", C.c_uint64), ("seconds", C.c_double),
+        ("busy_inflate_s", C.c_double), ("busy_parse_s", C.c_double), ("busy_stage_s", C.c_double),
+        ("busy_classify_s", C.c_double), ("busy_serialise_s", C.c_double), ("busy_compress_s", C.c_double),
+        ("busy_write_s", C.c_double), ("threads_inflate", C.c_int32), ("threads_compress", C.c_int32),
     ]
 
 

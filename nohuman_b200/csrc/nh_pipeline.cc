@@ -45,6 +45,7 @@
 #include <condition_variable>
 #include <deque>
 #include <algorithm>
+#include <atomic>
 #include <map>
 #include <memory>
 #include <unordered_map>
@@ -65,6 +66,27 @@ constexpr uint64_t NH_CHUNK_BASES = 48u << 20;  /* ... or this many bases in the
 constexpr size_t NH_CHUNK_TEXT = 1u << 30;      /* ... or this much header + sequence + quality text */
 constexpr uint64_t NH_BATCH_BASES = 64u << 20;  /* bases per nh_classify_batch call (session capacity; grows for a longer single unit) */
 constexpr size_t NH_OUT_BLOCK = 1u << 20;     /* uncompressed bytes per compression block */
+
+/* ------------------------------------------------------------------ */
+/* busy time per pipeline stage (nh_run_stats_t.busy_*): what limits the file path is a host
+ * question, so every stage accounts for the time it actually works */
+enum Stage { ST_INFLATE = 0, ST_PARSE, ST_STAGE, ST_CLASSIFY, ST_SERIALISE, ST_COMPRESS, ST_WRITE, ST_COUNT };
+struct StageClock {
+  std::atomic<uint64_t> ns[ST_COUNT];
+  StageClock() {
+    for (auto &x : ns) x = 0;
+  }
+};
+static thread_local StageClock *t_clock = nullptr; /* set by every pipeline thread */
+struct Busy {
+  StageClock *c;
+  int st;
+  std::chrono::steady_clock::time_point t0;
+  Busy(StageClock *clk, int stage) : c(clk), st(stage), t0(std::chrono::steady_clock::now()) {}
+  ~Busy() {
+    if (c) c->ns[st] += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count();
+  }
+};
 
 /* ------------------------------------------------------------------ */
 /* small blocking queue                                                */
@@ -206,7 +228,8 @@ class GzipStream {
 class BgzfReader {
  public:
   ~BgzfReader() { close(); }
-  bool open(const std::string &path, int threads) {
+  bool open(const std::string &path, int threads, StageClock *clk) {
+    clk_ = clk;
     f_ = fopen(path.c_str(), "rb");
     if (!f_) return false;
     setvbuf(f_, nullptr, _IOFBF, 4u << 20);
@@ -276,7 +299,11 @@ class BgzfReader {
     for (;;) {
       auto b = std::make_shared<Blk>();
       b->raw.resize(1u << 20);
-      const long n = gs.read(&b->raw[0], b->raw.size());
+      long n;
+      {
+        Busy busy(clk_, ST_INFLATE);
+        n = gs.read(&b->raw[0], b->raw.size());
+      }
       if (n < 0) return fail();
       if (n == 0) break;
       b->raw.resize((size_t)n);
@@ -353,6 +380,7 @@ class BgzfReader {
         b = todo_.front();
         todo_.pop_front();
       }
+      Busy busy(clk_, ST_INFLATE);
       bool ok = true;
       size_t total = 0, at = 0;
       for (uint32_t len : b->clen) {
@@ -391,6 +419,7 @@ class BgzfReader {
     inflateEnd(&zs);
   }
   FILE *f_ = nullptr;
+  StageClock *clk_ = nullptr;
   std::thread producer_;
   std::vector<std::thread> workers_;
   std::mutex m_;
@@ -405,7 +434,9 @@ class BgzfReader {
 class InputStream {
  public:
   ~InputStream() { close(); }
-  bool open(const std::string &path, int threads, std::string &err) {
+  int inflate_threads() const { return bgzf_ ? bgzf_threads_ : 1; }
+  bool open(const std::string &path, int threads, std::string &err, StageClock *clk) {
+    clk_ = clk;
     FILE *f = fopen(path.c_str(), "rb");
     if (!f) {
       err = "cannot open " + path;
@@ -418,7 +449,8 @@ class InputStream {
       /* blocked gzip: members inflated in parallel */
       fclose(f);
       bgzf_.reset(new BgzfReader());
-      if (!bgzf_->open(path, threads)) {
+      bgzf_threads_ = threads;
+      if (!bgzf_->open(path, threads, clk)) {
         err = "cannot open " + path;
         return false;
       }
@@ -531,11 +563,14 @@ class InputStream {
       }
       b->resize(BUF);
       long n;
-      if (kind_ == 'g') {
-        n = gz_.read(&(*b)[0], BUF);
-      } else {
-        const size_t r = fread(&(*b)[0], 1, BUF, file_);
-        n = (r == 0 && ferror(file_)) ? -1 : (long)r;
+      {
+        Busy busy(clk_, ST_INFLATE);
+        if (kind_ == 'g') {
+          n = gz_.read(&(*b)[0], BUF);
+        } else {
+          const size_t r = fread(&(*b)[0], 1, BUF, file_);
+          n = (r == 0 && ferror(file_)) ? -1 : (long)r;
+        }
       }
       if (n == 0 && kind_ == 'b') {
         /* a truncated or corrupt .bz2 shows only in the exit status of the child */
@@ -559,6 +594,8 @@ class InputStream {
   }
 
   std::unique_ptr<BgzfReader> bgzf_;
+  int bgzf_threads_ = 0;
+  StageClock *clk_ = nullptr;
   GzipStream gz_;
   FILE *file_ = nullptr;
   int kind_ = 'u';
@@ -591,14 +628,26 @@ struct Chunk {
 
 class RecordReader {
  public:
-  bool open(const std::string &path, int threads, std::string &err) {
+  bool open(const std::string &path, int threads, std::string &err, StageClock *clk) {
     path_ = path;
-    return in_.open(path, threads, err);
+    clk_ = clk;
+    return in_.open(path, threads, err, clk);
   }
+  int inflate_threads() const { return in_.inflate_threads(); }
   /* Fills `c`; c.last set at EOF.  With want_records == 0 the reader cuts the chunk itself (records,
    * bases or text bound); otherwise it reads exactly that many records (the second mate file follows
    * the cuts of the first, so mates always sit in the same Work). */
   void next_chunk(Chunk &c, size_t want_records = 0) {
+    const auto t_begin = std::chrono::steady_clock::now();
+    wait_ns_ = 0;
+    struct Account { /* parse time = time in here minus the time spent waiting for inflated bytes */
+      RecordReader *r;
+      std::chrono::steady_clock::time_point t0;
+      ~Account() {
+        const uint64_t all = (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count();
+        if (r->clk_) r->clk_->ns[ST_PARSE] += all > r->wait_ns_ ? all - r->wait_ns_ : 0;
+      }
+    } account{this, t_begin};
     c.text.clear();
     c.recs.clear();
     c.bases = 0;
@@ -626,7 +675,9 @@ class RecordReader {
       }
       c.fastq = format_ == 'q';
       Rec r{};
-      if (format_ == 'q') {
+      if (format_ == 'q' && fast_fastq(c, r)) {
+        /* whole record inside the current buffer: taken with four memchr calls */
+      } else if (format_ == 'q') {
         std::string *t = &c.text;
         size_t h0 = t->size();
         if (!getline_strip(*t)) {
@@ -699,7 +750,9 @@ class RecordReader {
  private:
   bool fill() {
     if (eof_) return false;
+    const auto w0 = std::chrono::steady_clock::now();
     long n = in_.next(buf_);
+    wait_ns_ += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - w0).count();
     if (n < 0) {
       io_error_ = true;
       eof_ = true;
@@ -716,6 +769,41 @@ class RecordReader {
   int peek() {
     if (pos_ >= end_ && !fill()) return -1;
     return (unsigned char)buf_[pos_];
+  }
+  /* FASTQ fast path: the four lines of the next record lie completely inside buf_ and the header
+   * starts with '@'.  Same result as the general path below (trailing whitespace stripped, '+' line
+   * dropped); anything unusual - a buffer border, an empty or malformed header - returns false with
+   * nothing consumed and the general path decides. */
+  bool fast_fastq(Chunk &c, Rec &r) {
+    if (pos_ >= end_) return false;
+    const char *p = &buf_[pos_], *e = &buf_[0] + end_;
+    if (*p != '@') return false;
+    const char *l1 = (const char *)memchr(p, '\n', (size_t)(e - p));
+    if (!l1) return false;
+    const char *l2 = (const char *)memchr(l1 + 1, '\n', (size_t)(e - l1 - 1));
+    if (!l2) return false;
+    const char *l3 = (const char *)memchr(l2 + 1, '\n', (size_t)(e - l2 - 1));
+    if (!l3) return false;
+    const char *l4 = (const char *)memchr(l3 + 1, '\n', (size_t)(e - l3 - 1));
+    if (!l4) return false;
+    auto rstrip = [](const char *b, const char *en) {
+      while (en > b && isspace((unsigned char)en[-1])) en--;
+      return en;
+    };
+    const char *he = rstrip(p, l1), *se = rstrip(l1 + 1, l2), *qe = rstrip(l3 + 1, l4);
+    if (he == p) return false;
+    std::string &t = c.text;
+    r.hdr_off = t.size();
+    r.hdr_len = (uint32_t)(he - p);
+    t.append(p, (size_t)(he - p));
+    r.seq_off = t.size();
+    r.seq_len = (uint32_t)(se - (l1 + 1));
+    t.append(l1 + 1, (size_t)(se - (l1 + 1)));
+    r.qual_off = t.size();
+    r.qual_len = (uint32_t)(qe - (l3 + 1));
+    t.append(l3 + 1, (size_t)(qe - (l3 + 1)));
+    pos_ = (size_t)(l4 + 1 - &buf_[0]);
+    return true;
   }
   /* appends the next line without its terminator and trailing whitespace; false at EOF with nothing read */
   bool getline_strip(std::string &out) {
@@ -741,6 +829,8 @@ class RecordReader {
   }
 
   InputStream in_;
+  StageClock *clk_ = nullptr;
+  uint64_t wait_ns_ = 0;
   std::string path_;
   std::string buf_;
   size_t pos_ = 0, end_ = 0;
@@ -940,7 +1030,7 @@ struct Block {
 
 class BlockWriter {
  public:
-  BlockWriter(OutputFile *files, int n_files, int threads) : files_(files), n_files_(n_files) {
+  BlockWriter(OutputFile *files, int n_files, int threads, StageClock *clk) : files_(files), n_files_(n_files), clk_(clk) {
     int n = threads < 1 ? 1 : threads;
     for (int i = 0; i < n; i++) workers_.emplace_back([this] { work(); });
     flusher_ = std::thread([this] { flush(); });
@@ -981,7 +1071,11 @@ class BlockWriter {
         b = todo_.front();
         todo_.pop_front();
       }
-      bool ok = files_[b->file].compress_block(b->raw, b->packed);
+      bool ok;
+      {
+        Busy busy(clk_, ST_COMPRESS);
+        ok = files_[b->file].compress_block(b->raw, b->packed);
+      }
       std::lock_guard<std::mutex> lk(m_);
       if (!ok) ok_ = false;
       b->raw.clear();
@@ -1002,6 +1096,7 @@ class BlockWriter {
         space_.notify_all();
       }
       const std::string &s = files_[b->file].parallel() ? b->packed : b->raw;
+      Busy busy(clk_, ST_WRITE);
       if (!files_[b->file].write(s)) {
         std::lock_guard<std::mutex> lk(m_);
         ok_ = false;
@@ -1010,6 +1105,7 @@ class BlockWriter {
   }
   OutputFile *files_;
   int n_files_;
+  StageClock *clk_;
   std::mutex m_;
   std::condition_variable cv_, space_;
   std::deque<std::shared_ptr<Block>> order_, todo_;
@@ -1234,10 +1330,11 @@ static int run_pipeline(const Decider &dec, const nh_files_t *files, nh_run_stat
   const bool keep_human = dec.params.keep_human != 0;
 
   std::string err;
+  StageClock clock;
   RecordReader readers[2];
   /* inflate threads per input file (only blocked gzip can use more than one) */
   const int in_threads = std::max(1, std::min(8, threads / nf));
-  if (!readers[0].open(files->in1, in_threads, err) || (paired && !readers[1].open(files->in2, in_threads, err)))
+  if (!readers[0].open(files->in1, in_threads, err, &clock) || (paired && !readers[1].open(files->in2, in_threads, err, &clock)))
     return nh_set_error(NH_ERR_IO, "%s", err.c_str());
   OutputFile outs[2];
   /* like src/main.rs:342-346: one output gets all the threads, two share them */
@@ -1328,8 +1425,10 @@ static int run_pipeline(const Decider &dec, const nh_files_t *files, nh_run_stat
     return w;
   };
 
-  /* two classifier threads per GPU: one batch's copies overlap the other's kernel */
-  const int n_classifiers = dec.fixed_keep ? 1 : 2 * (int)dec.dbs.size();
+  /* at least two classifier threads per GPU, so that one batch's copies overlap the other's kernel;
+   * up to four when -t allows it, because the same threads re-serialise the kept records */
+  const int per_gpu = std::max(2, std::min(4, threads / 4));
+  const int n_classifiers = dec.fixed_keep ? 1 : per_gpu * (int)dec.dbs.size();
   live_classifiers = n_classifiers;
   uint64_t fixed_cursor = 0;
   std::vector<std::thread> classifier_threads;
@@ -1400,6 +1499,7 @@ static int run_pipeline(const Decider &dec, const nh_files_t *files, nh_run_stat
             uint64_t u0 = 0, runs_at = 0;
             while (w->error.empty() && u0 < w->n_units) {
               uint64_t o = 0, s = 0, u1 = u0;
+              Busy *staging = new Busy(&clock, ST_STAGE);
               for (; u1 < w->n_units; u1++) {
                 uint64_t ub = 0;
                 for (int f = 0; f < nf; f++) ub += w->c[f].recs[u1].seq_len;
@@ -1412,6 +1512,8 @@ static int run_pipeline(const Decider &dec, const nh_files_t *files, nh_run_stat
                 }
               }
               h_off[s] = o;
+              delete staging;
+              Busy classifying(&clock, ST_CLASSIFY);
               if (nh_classify_batch(sess, h_bases, h_off, s, w->call.data() + u0, w->keep.data() + u0, nullptr) != NH_OK)
                 w->error = std::string("classification failed: ") + nh_last_error();
               if (want_lines && w->error.empty()) {
@@ -1430,6 +1532,7 @@ static int run_pipeline(const Decider &dec, const nh_files_t *files, nh_run_stat
           }
         }
         if (w->error.empty() && w->n_units) {
+          Busy serialising(&clock, ST_SERIALISE);
           /* serialise here, in parallel across batches; the writer only restores the order */
           if (want_lines) {
             w->klines.reserve(w->n_units * 96);
@@ -1469,7 +1572,7 @@ static int run_pipeline(const Decider &dec, const nh_files_t *files, nh_run_stat
     });
 
   /* writer (this thread): batches in id order */
-  BlockWriter bw(outs, nf, threads);
+  BlockWriter bw(outs, nf, threads, &clock);
   uint64_t want = 0, total_units = 0, n_classified = 0, total_bases = 0;
   std::string pend[2];
   for (;;) {
@@ -1547,6 +1650,15 @@ static int run_pipeline(const Decider &dec, const nh_files_t *files, nh_run_stat
     stats->unclassified = total_units - n_classified;
     stats->bases = total_bases;
     stats->seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    stats->busy_inflate_s = 1e-9 * (double)clock.ns[ST_INFLATE];
+    stats->busy_parse_s = 1e-9 * (double)clock.ns[ST_PARSE];
+    stats->busy_stage_s = 1e-9 * (double)clock.ns[ST_STAGE];
+    stats->busy_classify_s = 1e-9 * (double)clock.ns[ST_CLASSIFY];
+    stats->busy_serialise_s = 1e-9 * (double)clock.ns[ST_SERIALISE];
+    stats->busy_compress_s = 1e-9 * (double)clock.ns[ST_COMPRESS];
+    stats->busy_write_s = 1e-9 * (double)clock.ns[ST_WRITE];
+    stats->threads_inflate = readers[0].inflate_threads() + (paired ? readers[1].inflate_threads() : 0);
+    stats->threads_compress = outs[0].parallel() ? threads : 0;
   }
   return NH_OK;
 }

@@ -579,6 +579,10 @@ int main(int argc, char **argv) {
   logmsg("INFO", "Output file written to: \"%s\"", out1.c_str());
   if (paired) logmsg("INFO", "Output file written to: \"%s\"", out2.c_str());
   logmsg("DEBUG", "%.3f s, %.2f Mbp", st.seconds, st.bases / 1e6);
+  logmsg("DEBUG", "busy seconds per stage (summed over its threads): inflate %.2f (%d thr), parse %.2f, stage %.2f, classify %.2f, "
+                  "serialise %.2f, compress %.2f (%d thr), write %.2f",
+         st.busy_inflate_s, st.threads_inflate, st.busy_parse_s, st.busy_stage_s, st.busy_classify_s, st.busy_serialise_s,
+         st.busy_compress_s, st.threads_compress, st.busy_write_s);
   for (auto *x : sessions) nh_session_destroy(x);
   for (auto *x : replicas) nh_db_close(x);
   logmsg("INFO", "Done.");
