@@ -994,8 +994,8 @@ k_stream_classify(const NhDbParams db, const NhBatchPtrs b, const NhScoreParams 
             if (i == sp.lane_taxa) atomicOr(&sm.overflow, 1u << own);
           }
         }
-        __syncwarp(); /* continuation queue written before it is read below */
       }
+      __syncwarp(); /* continuation queue and the runs queued by emit() are written before other lanes read them below */
       /* ---- 2. next 32 lookups: continuations first, then fresh runs ---- */
       const uint32_t n_cq = cq_n; /* <= 32: one per lane in flight at most */
       const uint32_t room = 32u - n_cq;
@@ -1204,6 +1204,7 @@ k_stream_classify(const NhDbParams db, const NhBatchPtrs b, const NhScoreParams 
      * tile before it in the same sequence; upstream counts that as ONE hit group (its
      * last_minimizer lives per mate, ambiguous stretches included). */
     {
+      __syncwarp(); /* last_min / first_min / groups of the other lanes are final */
       const uint32_t has_mask = __ballot_sync(FULL_MASK, has_runs);
       if (have && kind != NH_ROLE_DEFERRED && t.pos_begin != 0u && has_runs && ((sm.first_hit >> lane) & 1u)) {
         const uint32_t seq_lane = lane - t.pos_begin / (uint32_t)db.tile_pos; /* lane of the sequence's first tile */
