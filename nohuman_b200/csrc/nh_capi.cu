@@ -204,6 +204,15 @@ static int finish_db(nh_db *db, const uint64_t hdr[4]) {
   CUDA_TRY(cudaMemcpy(db->d_ext, db->h_ext.data(), I.node_count * 4, cudaMemcpyHostToDevice));
   P.parent = db->d_parent;
   P.ext_id = db->d_ext;
+  /* a read can hit at most node_count distinct taxa; k_score_big's shared table holds 16K of them */
+  if (I.node_count >= NH_BIG_HASH_SLOTS * 3 / 4) {
+    uint32_t slots = 1;
+    while (slots < 2 * I.node_count) slots <<= 1;
+    CUDA_TRY(cudaMalloc(&db->d_huge, ((size_t)2 * slots + 4) * 4));
+    CUDA_TRY(cudaMemset(db->d_huge, 0, ((size_t)2 * slots + 4) * 4));
+    P.huge_slots = slots;
+    P.huge_table = db->d_huge;
+  }
   cudaDeviceProp prop;
   CUDA_TRY(cudaGetDeviceProperties(&prop, db->info.device));
   db->sm_count = prop.multiProcessorCount;
@@ -591,6 +600,7 @@ extern "C" void nh_db_close(nh_db *db) {
   if (db->owns_cells && db->d_cells) cudaFree(db->d_cells);
   if (db->d_parent) cudaFree(db->d_parent);
   if (db->d_ext) cudaFree(db->d_ext);
+  if (db->d_huge) cudaFree(db->d_huge);
   delete db;
 }
 
@@ -859,7 +869,7 @@ extern "C" int nh_session_sync(nh_session *s, nh_batch_stats_t *stats) {
   CUDA_TRY(cudaSetDevice(s->db->info.device));
   CUDA_TRY(cudaStreamSynchronize(s->stream));
   if (s->pending && s->h_counters->error)
-    return nh_set_error(NH_ERR_UNSUPPORTED, "a read hit more than %d distinct taxa", NH_BIG_HASH_SLOTS);
+    return nh_set_error(NH_ERR_CUDA, "internal error: a unit's taxon table overflowed although it can hold the whole taxonomy");
   if (stats) {
     memset(stats, 0, sizeof *stats);
     if (s->pending) {

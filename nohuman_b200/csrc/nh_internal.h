@@ -29,6 +29,7 @@ struct nh_db {
   bool owns_cells = false;
   uint32_t *d_parent = nullptr;
   uint32_t *d_ext = nullptr;
+  uint32_t *d_huge = nullptr; /* global-memory taxon table for units with more distinct taxa than shared memory holds */
   std::vector<uint32_t> h_parent, h_ext;
   std::vector<uint64_t> h_ext64;
   std::vector<std::string> h_name, h_rank; /* taxo.k2d name / rank strings per node (reports) */

@@ -716,7 +716,26 @@ k_score_big(const NhDbParams db, const NhBatchPtrs b, const NhScoreParams sp) {
     acc_begin(keys, cnts, NH_BIG_HASH_SLOTS - 1u, lane);
     const UnitAcc a = acc_rescan(db, b, keys, cnts, NH_BIG_HASH_SLOTS - 1u, u, lane, s_min);
     if (!resolve_unit(db, b, sp, db.parent, keys, cnts, NH_BIG_HASH_SLOTS - 1u, u, lane, a, &classified, &kept)) {
-      if (lane == 0) atomicExch(&b.counters->error, 1u);
+      /* more than 16K distinct taxa in ONE read: the device's table in global memory can hold every
+       * node of the taxonomy; units this extreme take turns on it */
+      if (db.huge_slots == 0u) {
+        if (lane == 0) atomicExch(&b.counters->error, 1u); /* cannot happen: node_count fits the shared table */
+        continue;
+      }
+      uint32_t *gkeys = db.huge_table, *gcnts = db.huge_table + db.huge_slots, *lock = db.huge_table + 2u * db.huge_slots;
+      if (lane == 0)
+        while (atomicCAS(lock, 0u, 1u) != 0u) __nanosleep(200);
+      __syncwarp();
+      __threadfence();
+      acc_begin(gkeys, gcnts, db.huge_slots - 1u, lane);
+      const UnitAcc ga = acc_rescan(db, b, gkeys, gcnts, db.huge_slots - 1u, u, lane, s_min);
+      const bool ok = resolve_unit(db, b, sp, db.parent, gkeys, gcnts, db.huge_slots - 1u, u, lane, ga, &classified, &kept);
+      __threadfence();
+      __syncwarp();
+      if (lane == 0) {
+        atomicExch(lock, 0u);
+        if (!ok) atomicExch(&b.counters->error, 1u);
+      }
     }
   }
   if (lane == 0) {

@@ -43,6 +43,10 @@ struct NhDbParams {
   const uint32_t *parent;    /* node_count x u32 */
   const uint32_t *ext_id;    /* node_count x u32 */
   uint32_t node_count;
+  /* taxonomies with more nodes than k_score_big's shared table could ever need: one table in global
+   * memory per device, 2 x huge_slots words + a lock word, used by one unit at a time */
+  uint32_t huge_slots;       /* power of two >= 2 * node_count, or 0 */
+  uint32_t *huge_table;
 };
 
 struct __align__(16) NhTile {

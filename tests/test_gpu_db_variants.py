@@ -84,3 +84,32 @@ def test_taxonomy_larger_than_shared_memory(oracle, tmp_path):
     assert db.tax.node_count > 8192 and int(db.cht.value_bits) == 14
     check(db, path, True, paired=False, conf=0.05)
     check(db, path, True, paired=True, conf=0.5)
+
+
+def test_read_hitting_more_taxa_than_any_shared_table(oracle, tmp_path):
+    """17 000 leaf taxa with one 60 bp genome each and ONE read that runs through all of them: more
+    distinct taxa than the in-warp tables (8), k_score's (64) and k_score_big's shared table (16 384)
+    hold.  The unit is classified from the device's global-memory table instead of failing the run."""
+    from nohuman_b200 import Database, Session
+    rng = np.random.default_rng(41)
+    n_leaves = 17_000
+    tax = [oracle.TaxSpec(1, 1, "root", "no rank"), oracle.TaxSpec(2, 1, "clade", "no rank")]
+    tax += [oracle.TaxSpec(100 + i, 2, f"leaf{i}", "species") for i in range(n_leaves)]
+    genomes = [(100 + i, synth.random_genome(rng, 60)) for i in range(n_leaves)]
+    db = oracle.OracleDb.build([(t, bytes(g)) for t, g in genomes], tax, capacity=2_000_003)
+    d = str(tmp_path / "many_taxa")
+    db.save(d)
+    everything = np.concatenate([g for _, g in genomes])
+    seqs = [everything, everything[:300_000].copy(), genomes[5][1], np.concatenate([g for _, g in genomes[:40]])]
+    seqs += synth.illumina_reads(genomes[:2000], 300, 60, seed=3)
+    bases, offsets = synth.pack(seqs)
+    for conf in (0.0, 0.5):
+        db.confidence = conf
+        want = db.classify_batch(bases, offsets)
+        with Database.open(d, 0) as gdb, Session(gdb, confidence=conf, max_batch_bases=len(bases) + 4096) as sess:
+            call, keep, st = sess.classify(bases, offsets)
+            icall, tk, hg = sess.debug_last_batch(len(call))
+        np.testing.assert_array_equal(hg, want["hit_groups"])
+        np.testing.assert_array_equal(tk, want["total_kmers"])
+        np.testing.assert_array_equal(call, want["ext"])
+    assert want["hit_groups"][0] > 16_384
