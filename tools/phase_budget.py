@@ -55,8 +55,9 @@ for r in rows:
         continue
     if len(r) > 5 and r[0] == "Line No":
         hdr = {h: i for i, h in enumerate(r)}
+        ncol = len(r)
         continue
-    if not hdr or len(r) != len(hdr) or not r[0].strip().isdigit():
+    if not hdr or len(r) != ncol or not r[0].strip().isdigit():
         continue
     ln = int(r[0])
     text = r[1]
