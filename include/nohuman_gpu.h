@@ -163,8 +163,8 @@ int nh_classify_batch(nh_session *s, const uint8_t *bases, const uint64_t *offse
                       nh_batch_stats_t *stats);
 
 /* Same with DEVICE-resident input and output (all pointers are device
- * pointers on the session's device; d_bases must be readable up to the next
- * 16-byte boundary past total_bases).  Asynchronous on the session stream;
+ * pointers on the session's device; d_bases must be 16-byte aligned, as any
+ * cudaMalloc pointer is).  Asynchronous on the session stream;
  * call nh_session_sync before reading outputs or stats. */
 int nh_classify_batch_device(nh_session *s, const uint8_t *d_bases, const uint64_t *d_offsets,
                              uint64_t n_seqs, uint64_t total_bases, uint32_t *d_out_call,

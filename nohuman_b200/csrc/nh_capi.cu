@@ -902,6 +902,8 @@ extern "C" int nh_classify_batch_device(nh_session *s, const uint8_t *d_bases,
                                         uint64_t total_bases, uint32_t *d_out_call,
                                         uint8_t *d_out_keep) {
   if (!s || !d_bases || !d_offsets) return nh_set_error(NH_ERR_INVALID, "null argument");
+  if (((uintptr_t)d_bases & 15u) != 0) /* the streaming kernel stages bases with 16-byte asynchronous copies */
+    return nh_set_error(NH_ERR_INVALID, "d_bases must be 16-byte aligned");
   int rc = check_batch_args(s, n_seqs, total_bases);
   if (rc) return rc;
   CUDA_TRY(cudaSetDevice(s->db->info.device));
