@@ -53,7 +53,7 @@ struct __align__(16) NhTile {
   uint32_t seq;       /* sequence index in the batch */
   uint32_t pos_begin; /* first k-mer position of the tile */
   uint32_t slot;      /* first lookup slot of the tile = k-mer positions before it in the batch */
-  uint32_t role;      /* who scores the tile's unit inside k_scan_probe_score, NH_ROLE_* */
+  uint32_t role;      /* who scores the tile's unit inside k_stream_classify, NH_ROLE_* */
 };
 
 /* role of a tile in the streaming kernel: a unit (read or pair) is scored inside the warp when all
