@@ -162,6 +162,23 @@ int nh_classify_batch(nh_session *s, const uint8_t *bases, const uint64_t *offse
                       uint64_t n_seqs, uint32_t *out_call, uint8_t *out_keep,
                       nh_batch_stats_t *stats);
 
+/* ---- packed transfer format: 0.4 bytes per base over PCIe instead of 1 ----
+ * Every sequence starts on a UNIT of 32 bases.  codes: 8 bytes per unit, 2 bits per base (A 0, C 1,
+ * G 2, T 3, either case), 4 bases per byte, first base in the top bits; valid: one 32-bit word per
+ * unit, bit j = base j of the unit is an unambiguous base of the sequence (LSB first; padding and
+ * every other byte value: 0); poff[n_seqs+1]: first unit of each sequence.
+ * nh_packed_units gives the number of units a batch needs; nh_pack_reads fills the three arrays
+ * (codes: units*8 bytes, valid: units words, poff: n_seqs+1) from ASCII with `threads` host
+ * threads (AVX2 when the CPU has it).  nh_classify_batch_packed is nh_classify_batch for such input
+ * (sessions without emit_runs, databases the streaming kernel covers); offsets still gives the
+ * sequence lengths.  Same per-unit results as the ASCII entry point. */
+int nh_packed_units(const uint64_t *offsets, uint64_t n_seqs, uint64_t *out_units);
+int nh_pack_reads(const uint8_t *bases, const uint64_t *offsets, uint64_t n_seqs, uint8_t *codes, uint32_t *valid,
+                  uint32_t *poff, int threads);
+int nh_classify_batch_packed(nh_session *s, const uint8_t *codes, const uint32_t *valid, const uint32_t *poff,
+                             const uint64_t *offsets, uint64_t n_seqs, uint32_t *out_call, uint8_t *out_keep,
+                             nh_batch_stats_t *stats);
+
 /* Same with DEVICE-resident input and output (all pointers are device
  * pointers on the session's device; d_bases must be 16-byte aligned, as any
  * cudaMalloc pointer is).  Asynchronous on the session stream;

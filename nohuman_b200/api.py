@@ -63,6 +63,26 @@ def rewrite_files(keep: np.ndarray, call_ext: np.ndarray, in1, out1, in2=None, o
     return st
 
 
+def packed_units(offsets: np.ndarray) -> int:
+    offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+    n = C.c_uint64()
+    check(lib().nh_packed_units(offsets.ctypes.data, len(offsets) - 1, C.byref(n)))
+    return int(n.value)
+
+
+def pack_reads(bases: np.ndarray, offsets: np.ndarray, threads: int = 1):
+    """ASCII -> (codes u8[units*8], valid u32[units], poff u32[n_seqs+1]) on the host (nh_pack_reads, no GPU needed)."""
+    bases = np.ascontiguousarray(bases, dtype=np.uint8)
+    offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+    units = packed_units(offsets)
+    codes = np.zeros(units * 8 + 16, np.uint8)
+    valid = np.zeros(units + 4, np.uint32)
+    poff = np.zeros(len(offsets), np.uint32)
+    check(lib().nh_pack_reads(bases.ctypes.data, offsets.ctypes.data, len(offsets) - 1, codes.ctypes.data, valid.ctypes.data,
+                              poff.ctypes.data, threads))
+    return codes, valid, poff
+
+
 class Database:
     """A kraken2 database (hash.k2d / opts.k2d / taxo.k2d) resident in HBM."""
 
@@ -180,6 +200,27 @@ class Session:
         st = BatchStats()
         check(lib().nh_classify_batch(self._h, bases_ptr, offsets_ptr, n_seqs, call_ptr, keep_ptr,
                                       C.byref(st)))
+        return st
+
+    # -- packed transfer format (2-bit codes + validity bits, 0.4 B/base over PCIe) ---------
+    def classify_packed(self, bases: np.ndarray, offsets: np.ndarray, threads: int = 1):
+        """pack_reads on the host, then nh_classify_batch_packed; same results as classify()."""
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        codes, valid, poff = pack_reads(bases, offsets, threads)
+        n_seqs = len(offsets) - 1
+        n_units = n_seqs // 2 if self.paired else n_seqs
+        call = np.zeros(n_units, np.uint32)
+        keep = np.zeros(n_units, np.uint8)
+        st = BatchStats()
+        check(lib().nh_classify_batch_packed(self._h, codes.ctypes.data, valid.ctypes.data, poff.ctypes.data,
+                                             offsets.ctypes.data, n_seqs, call.ctypes.data, keep.ctypes.data, C.byref(st)))
+        return call, keep, st
+
+    def classify_packed_raw(self, codes_ptr: int, valid_ptr: int, poff_ptr: int, offsets_ptr: int, n_seqs: int,
+                            call_ptr: int, keep_ptr: int) -> BatchStats:
+        st = BatchStats()
+        check(lib().nh_classify_batch_packed(self._h, codes_ptr, valid_ptr, poff_ptr, offsets_ptr, n_seqs, call_ptr,
+                                             keep_ptr, C.byref(st)))
         return st
 
     # -- device-resident (asynchronous on the session stream) ---------

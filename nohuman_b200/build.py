@@ -16,7 +16,7 @@ LIB = os.path.join(PKG, "libnohuman_gpu.so")
 CLI = os.path.join(PKG, "bin", "nohuman")
 
 CU_SOURCES = ["nh_kernels.cu", "nh_capi.cu", "nh_synth.cu"]
-CC_SOURCES = ["nh_pipeline.cc"]  # host pipeline, compiled into the same library
+CC_SOURCES = ["nh_pipeline.cc", "nh_pack.cc"]  # host pipeline and the host-side packer, compiled into the same library
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

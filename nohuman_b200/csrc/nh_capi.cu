@@ -742,6 +742,9 @@ extern "C" void nh_session_destroy(nh_session *s) {
   cudaFree(s->d_run_len);
   cudaFree(s->d_tile_run_off);
   cudaFree(s->d_run_cursor);
+  cudaFree(s->d_codes);
+  cudaFree(s->d_valid);
+  cudaFree(s->d_poff);
   if (s->h_counters) cudaFreeHost(s->h_counters);
   for (int i = 0; i < NH_NUM_EVENTS; i++)
     if (s->ev[i]) cudaEventDestroy(s->ev[i]);
@@ -776,12 +779,18 @@ static int enqueue_batch(nh_session *s, const uint8_t *d_bases, const uint64_t *
   if (s->use_fused) {
     const uint64_t mean_len = n_seqs ? total_bases / n_seqs : 0;
     s->P.tile_pos = s->forced_tile_pos ? s->forced_tile_pos : (mean_len > 1000 ? NH_FUSED_TILE_POS_LONG : NH_FUSED_TILE_POS);
+    if (s->packed_next) s->P.tile_pos = std::max(32, s->P.tile_pos & ~31); /* tiles of packed input start on a unit of 32 bases */
   }
   const NhDbParams &P = s->P;
   NhBatchPtrs B;
   memset(&B, 0, sizeof B);
   B.bases = d_bases;
   B.offsets = d_offsets;
+  if (s->packed_next) {
+    B.codes = s->d_codes;
+    B.valid = s->d_valid;
+    B.poff = s->d_poff;
+  }
   B.n_seqs = (uint32_t)n_seqs;
   B.paired = s->params.paired ? 1 : 0;
   B.n_units = (uint32_t)(B.paired ? n_seqs / 2 : n_seqs);
@@ -938,6 +947,56 @@ extern "C" int nh_classify_batch(nh_session *s, const uint8_t *bases, const uint
   CUDA_TRY(cudaMemcpyAsync(s->d_offsets, offsets, (n_seqs + 1) * 8, cudaMemcpyHostToDevice, st));
   rc = enqueue_batch(s, s->d_bases, s->d_offsets, n_seqs, total, s->d_out_call, s->d_out_keep, true,
                      nullptr, nullptr, nullptr);
+  if (rc) return rc;
+  if (out_call) CUDA_TRY(cudaMemcpyAsync(out_call, s->d_out_call, n_units * 4, cudaMemcpyDeviceToHost, st));
+  if (out_keep) CUDA_TRY(cudaMemcpyAsync(out_keep, s->d_out_keep, n_units, cudaMemcpyDeviceToHost, st));
+  cudaEventRecord(s->ev[EV_D2H1], st);
+  s->timed_copies = true;
+  return nh_session_sync(s, stats);
+}
+
+/* Packed host input: 2-bit codes + validity bits + unit offsets (nh_pack_reads) instead of ASCII.
+ * 0.4 bytes per base cross PCIe; the kernel instantiation that reads the planes also skips the
+ * ASCII -> 2-bit step. */
+extern "C" int nh_classify_batch_packed(nh_session *s, const uint8_t *codes, const uint32_t *valid, const uint32_t *poff,
+                                        const uint64_t *offsets, uint64_t n_seqs, uint32_t *out_call, uint8_t *out_keep,
+                                        nh_batch_stats_t *stats) {
+  if (!s || !offsets || !poff || (n_seqs && offsets[n_seqs] > 0 && (!codes || !valid)))
+    return nh_set_error(NH_ERR_INVALID, "null argument");
+  if (!s->use_fused) return nh_set_error(NH_ERR_UNSUPPORTED, "packed input needs the streaming kernel (window of 5 l-mers)");
+  if (s->params.emit_runs) return nh_set_error(NH_ERR_UNSUPPORTED, "packed input is not available to sessions created with emit_runs");
+  const uint64_t total = n_seqs ? offsets[n_seqs] - offsets[0] : 0;
+  if (n_seqs && offsets[0] != 0) return nh_set_error(NH_ERR_INVALID, "offsets[0] must be 0");
+  int rc = check_batch_args(s, n_seqs, total);
+  if (rc) return rc;
+  CUDA_TRY(cudaSetDevice(s->db->info.device));
+  if (n_seqs == 0) {
+    s->pending = false;
+    if (stats) memset(stats, 0, sizeof *stats);
+    return NH_OK;
+  }
+  const uint64_t units = poff[n_seqs];
+  const uint64_t cap_units = s->cap_bases / 32 + s->cap_seqs + 1;
+  if (units > cap_units) return nh_set_error(NH_ERR_CAPACITY, "packed batch has %llu units, session holds %llu", (unsigned long long)units, (unsigned long long)cap_units);
+  if (!s->d_codes) { /* allocated on the first packed batch */
+    cudaError_t e = cudaMalloc(&s->d_codes, cap_units * 8 + 64);
+    if (e == cudaSuccess) e = cudaMalloc(&s->d_valid, cap_units * 4 + 64);
+    if (e == cudaSuccess) e = cudaMalloc(&s->d_poff, (s->cap_seqs + 1) * 4);
+    if (e != cudaSuccess) return nh_set_error(NH_ERR_NOMEM, "allocating the packed input planes failed: %s", cudaGetErrorString(e));
+    s->device_bytes += cap_units * 12 + 128 + (s->cap_seqs + 1) * 4;
+  }
+  cudaStream_t st = s->stream;
+  const uint64_t n_units = s->params.paired ? n_seqs / 2 : n_seqs;
+  cudaEventRecord(s->ev[EV_H2D0], st);
+  if (units) {
+    CUDA_TRY(cudaMemcpyAsync(s->d_codes, codes, units * 8, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(s->d_valid, valid, units * 4, cudaMemcpyHostToDevice, st));
+  }
+  CUDA_TRY(cudaMemcpyAsync(s->d_poff, poff, (n_seqs + 1) * 4, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(s->d_offsets, offsets, (n_seqs + 1) * 8, cudaMemcpyHostToDevice, st));
+  s->packed_next = true;
+  rc = enqueue_batch(s, nullptr, s->d_offsets, n_seqs, total, s->d_out_call, s->d_out_keep, true, nullptr, nullptr, nullptr);
+  s->packed_next = false;
   if (rc) return rc;
   if (out_call) CUDA_TRY(cudaMemcpyAsync(out_call, s->d_out_call, n_units * 4, cudaMemcpyDeviceToHost, st));
   if (out_keep) CUDA_TRY(cudaMemcpyAsync(out_keep, s->d_out_keep, n_units, cudaMemcpyDeviceToHost, st));

@@ -58,6 +58,9 @@ struct nh_session {
   uint32_t *d_deferred = nullptr;
   uint32_t *d_run_ext = nullptr, *d_tile_run_off = nullptr, *d_run_cursor = nullptr;
   uint16_t *d_run_len = nullptr;
+  uint8_t *d_codes = nullptr;  /* packed input planes (nh_classify_batch_packed), allocated on first use */
+  uint32_t *d_valid = nullptr, *d_poff = nullptr;
+  bool packed_next = false;    /* the batch being enqueued came packed */
   uint64_t last_seqs = 0;
   bool use_fused = false, last_fused = false;
   int lane_taxa = NH_LANE_TAXA;

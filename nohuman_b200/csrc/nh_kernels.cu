@@ -220,19 +220,27 @@ __device__ __forceinline__ uint32_t minimizer_tile(const NhDbParams &db, const N
   const uint32_t nb = npos + (uint32_t)k - 1u; /* bases of this tile */
   const uint32_t nq = npos + (uint32_t)w - 1u; /* l-mers of this tile */
 
-  /* -- load + 2-bit pack: 8 bases per lane, 8-byte aligned loads -- */
+  /* -- load + 2-bit pack: 8 bases per lane, 8-byte aligned loads (or 2 code bytes + 1 validity byte of packed input) -- */
   const uint8_t *g = b.bases + so + t.pos_begin;
-  const uint32_t shift = (uint32_t)((uintptr_t)g & 7u);
+  const uint64_t pbase = b.codes ? (uint64_t)b.poff[t.seq] * 32ULL + t.pos_begin : 0ULL; /* base index in the packed planes */
+  const uint32_t shift = b.codes ? (uint32_t)(pbase & 7ULL) : (uint32_t)((uintptr_t)g & 7u);
   const uint8_t *ga = g - shift;
   const uint32_t nchunks = (shift + nb + 7u) >> 3;
   uint32_t half = 0, amb8 = 0;
   if (lane < nchunks) {
-    uint2 v = __ldg(reinterpret_cast<const uint2 *>(ga) + lane);
-    uint32_t a0, a1;
-    uint32_t p0 = nh_pack4(v.x, &a0);
-    uint32_t p1 = nh_pack4(v.y, &a1);
-    half = (p0 << 8) | p1;
-    amb8 = a0 | (a1 << 4);
+    if (b.codes) {
+      const uint64_t first = (pbase - shift) + 8ULL * lane; /* a multiple of 8 */
+      const uint32_t c2 = *reinterpret_cast<const uint16_t *>(b.codes + (first >> 2));
+      half = ((c2 & 0xFFu) << 8) | (c2 >> 8);
+      amb8 = (~(uint32_t)reinterpret_cast<const uint8_t *>(b.valid)[first >> 3]) & 0xFFu;
+    } else {
+      uint2 v = __ldg(reinterpret_cast<const uint2 *>(ga) + lane);
+      uint32_t a0, a1;
+      uint32_t p0 = nh_pack4(v.x, &a0);
+      uint32_t p1 = nh_pack4(v.y, &a1);
+      half = (p0 << 8) | p1;
+      amb8 = a0 | (a1 << 4);
+    }
     /* keep only ambiguity bits of bases inside [shift, shift + nb) */
     int lo = (int)shift - (int)(lane * 8u);
     int hi = (int)(shift + nb) - (int)(lane * 8u);
@@ -824,6 +832,13 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
+/* 8 and 4 bytes (packed input: one unit's codes and validity word) */
+__device__ __forceinline__ void cp_async8(uint32_t dst, const void *src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void *src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
 /* the same with only the first n_src bytes taken from global memory and the rest zero-filled */
 __device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void *src, uint32_t n_src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(n_src) : "memory");
@@ -860,8 +875,10 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
 #endif
 
 /* KL = 1: kraken2's default k = 35, l = 31 compiled in (shift counts and thresholds become
- * immediates); KL = 0: any k, l with k - l + 1 = W, read from the database */
-template <int W, int KL, bool DBG, bool REV0, bool EMIT>
+ * immediates); KL = 0: any k, l with k - l + 1 = W, read from the database.
+ * PACKED: the batch came as 2-bit codes + validity bits (nh_classify_batch_packed), every sequence
+ * starting on a unit of 32 bases; tiles then start on units too (tile_pos is a multiple of 32). */
+template <int W, int KL, bool DBG, bool REV0, bool EMIT, bool PACKED>
 __global__ void __launch_bounds__(NH_BLOCK_THREADS, NH_STREAM_MIN_BLOCKS)
 k_stream_classify(const NhDbParams db, const NhBatchPtrs b, const NhScoreParams sp) {
   static_assert(W == 5, "the scan consumes one 4-byte word per ring rotation");
@@ -1078,9 +1095,9 @@ k_stream_classify(const NhDbParams db, const NhBatchPtrs b, const NhScoreParams 
         if (npos > (uint32_t)db.tile_pos) npos = (uint32_t)db.tile_pos;
         nb = npos + (uint32_t)k - 1u;
       }
-      const uint8_t *g = b.bases + so + t.pos_begin;
-      const uint32_t mis = (uint32_t)((uintptr_t)g & 3u);
-      const uint32_t my_words = have ? (mis + nb + 3u) >> 2 : 0u;
+      const uint8_t *g = PACKED ? nullptr : b.bases + so + t.pos_begin;
+      const uint32_t mis = PACKED ? 0u : (uint32_t)((uintptr_t)g & 3u);
+      const uint32_t my_words = have ? (mis + nb + 3u) >> 2 : 0u; /* groups of four bases */
       const uint32_t max_words = __reduce_max_sync(FULL_MASK, my_words);
 
       uint64_t fwd = 0, rc = 0;
@@ -1121,9 +1138,7 @@ k_stream_classify(const NhDbParams db, const NhBatchPtrs b, const NhScoreParams 
        * Bytes outside the tile never get here as bases: the staging zero-fills what lies past the
        * tile's end and the head of the first word is cleared below, and a zero byte is an ambiguous
        * base - it resets the l-mer and cannot end a k-mer. */
-      auto scan_word = [&](const uint32_t word, const uint32_t base_i) {
-        uint32_t ambs;
-        const uint32_t codes = nh_pack4(word, &ambs); /* first base in bits 7..6 */
+      auto scan_quad = [&](const uint32_t codes /* first base in bits 7..6 */, const uint32_t ambs, const uint32_t base_i) {
 #pragma unroll
         for (int j = 0; j < 4; j++) {
           const uint32_t i = base_i + (uint32_t)j; /* index in the word-aligned stream */
@@ -1164,6 +1179,50 @@ k_stream_classify(const NhDbParams db, const NhBatchPtrs b, const NhScoreParams 
         }
       };
 
+      auto scan_word = [&](const uint32_t word, const uint32_t base_i) {
+        uint32_t ambs;
+        const uint32_t codes = nh_pack4(word, &ambs);
+        scan_quad(codes, ambs, base_i);
+      };
+
+      if (PACKED) {
+        /* one chunk = one unit of 32 bases: 8 code bytes + 1 validity word per lane, double-buffered */
+        const uint64_t unit0 = have ? (uint64_t)b.poff[t.seq] + (t.pos_begin >> 5) : 0ULL;
+        const uint32_t my_units = have ? (nb + 31u) >> 5 : 0u;
+        const uint32_t n_chunks = (max_words + 7u) >> 3;
+        auto stage = [&](const uint32_t ch) {
+          const uint32_t buf = ch & 1u;
+          const uint32_t dst = win0 + buf * (32u * NH_BCHUNK_STRIDE);
+          if (ch < my_units) {
+            cp_async8(dst, b.codes + (unit0 + ch) * 8ULL);
+            cp_async4(dst + 8u, b.valid + unit0 + ch);
+          }
+          cp_async_arrive(bar0 + buf * 8u);
+        };
+        if (n_chunks) stage(0u);
+        for (uint32_t ch = 0; ch < n_chunks; ch++) {
+          if (ch + 1u < n_chunks) stage(ch + 1u);
+          const uint32_t buf = ch & 1u;
+          mbar_wait(bar0 + buf * 8u, (bar_par >> buf) & 1u);
+          bar_par ^= 1u << buf;
+          const uint32_t wbase = win0 + buf * (32u * NH_BCHUNK_STRIDE);
+          const uint32_t c_lo = lds_u32(wbase), c_hi = lds_u32(wbase + 4u);
+          uint32_t vw = lds_u32(wbase + 8u);
+          /* bases past the tile's end (the next tile's, or stale bytes of a lane that is done) are ambiguous */
+          const int rem = (int)nb - (int)(ch * 32u);
+          vw = rem <= 0 ? 0u : (rem >= 32 ? vw : vw & ((1u << rem) - 1u));
+          const uint32_t amb_w = ~vw;
+          const uint32_t q0 = ch * 8u;
+          const uint32_t qn = max_words - q0 < 8u ? max_words - q0 : 8u;
+#pragma unroll 1
+          for (uint32_t qd = 0; qd < qn; qd++) {
+            const uint32_t cw = qd < 4u ? c_lo : c_hi;
+            scan_quad((cw >> ((qd & 3u) * 8u)) & 0xFFu, (amb_w >> (qd * 4u)) & 0xFu, (q0 + qd) * 4u);
+          }
+          __syncwarp();
+        }
+        emit(cnt != 0u, last, cnt);
+      } else {
       /* the lane's window for chunk c: bytes [32c, 32c + 48) from src0, the 16-byte block holding word 0 */
       const uint8_t *q = g - mis;
       const uint32_t a16 = (uint32_t)((uintptr_t)q & 15u);
@@ -1204,6 +1263,7 @@ k_stream_classify(const NhDbParams db, const NhBatchPtrs b, const NhScoreParams 
         __syncwarp(); /* every lane is done with this buffer before chunk ch + 2 lands in it */
       }
       emit(cnt != 0u, last, cnt);
+      } /* !PACKED */
     }
     const bool has_runs = first_flag == 0u;
     if (EMIT && have) {
@@ -1511,13 +1571,16 @@ cudaError_t nh_kernels_init(void) {
 #define NH_SET_SMEM(kern, bytes)                                                             \
   e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);       \
   if (e != cudaSuccess) return e;
-  NH_SET_SMEM((k_stream_classify<5, 1, false, false, false>), smax)
-  NH_SET_SMEM((k_stream_classify<5, 1, false, false, true>), smax_emit)
-  NH_SET_SMEM((k_stream_classify<5, 0, false, false, false>), smax)
-  NH_SET_SMEM((k_stream_classify<5, 0, false, true, false>), smax)
-  NH_SET_SMEM((k_stream_classify<5, 0, true, false, false>), smax)
-  NH_SET_SMEM((k_stream_classify<5, 0, false, false, true>), smax_emit)
-  NH_SET_SMEM((k_stream_classify<5, 0, false, true, true>), smax_emit)
+  NH_SET_SMEM((k_stream_classify<5, 1, false, false, false, false>), smax)
+  NH_SET_SMEM((k_stream_classify<5, 1, false, false, true, false>), smax_emit)
+  NH_SET_SMEM((k_stream_classify<5, 0, false, false, false, false>), smax)
+  NH_SET_SMEM((k_stream_classify<5, 0, false, true, false, false>), smax)
+  NH_SET_SMEM((k_stream_classify<5, 0, true, false, false, false>), smax)
+  NH_SET_SMEM((k_stream_classify<5, 0, false, false, true, false>), smax_emit)
+  NH_SET_SMEM((k_stream_classify<5, 0, false, true, true, false>), smax_emit)
+  NH_SET_SMEM((k_stream_classify<5, 1, false, false, false, true>), smax)
+  NH_SET_SMEM((k_stream_classify<5, 0, false, false, false, true>), smax)
+  NH_SET_SMEM((k_stream_classify<5, 0, false, true, false, true>), smax)
 #undef NH_SET_SMEM
   return cudaSuccess;
 }
@@ -1549,20 +1612,21 @@ int nh_launch_stream(const NhDbParams &db, const NhBatchPtrs &b, const NhScorePa
   /* kraken2's defaults (k 35, l 31, current reverse-complement) get the instantiation with the
    * constants compiled in; anything else with a window of 5 takes the generic one */
   const bool kl_default = db.k == 35 && db.l == 31 && db.revcom_version != 0;
-  if (b.dbg_pos_min != nullptr) /* nh_debug_minimizers (never with emit_runs) */
-    k_stream_classify<5, 0, true, false, false><<<grid, NH_BLOCK_THREADS, smem, st>>>(db, b, sp);
-  else if (kl_default && emit)
-    k_stream_classify<5, 1, false, false, true><<<grid, NH_BLOCK_THREADS, smem, st>>>(db, b, sp);
-  else if (kl_default)
-    k_stream_classify<5, 1, false, false, false><<<grid, NH_BLOCK_THREADS, smem, st>>>(db, b, sp);
-  else if (db.revcom_version == 0 && emit)
-    k_stream_classify<5, 0, false, true, true><<<grid, NH_BLOCK_THREADS, smem, st>>>(db, b, sp);
-  else if (db.revcom_version == 0)
-    k_stream_classify<5, 0, false, true, false><<<grid, NH_BLOCK_THREADS, smem, st>>>(db, b, sp);
-  else if (emit)
-    k_stream_classify<5, 0, false, false, true><<<grid, NH_BLOCK_THREADS, smem, st>>>(db, b, sp);
-  else
-    k_stream_classify<5, 0, false, false, false><<<grid, NH_BLOCK_THREADS, smem, st>>>(db, b, sp);
+#define NH_LAUNCH(KLv, DBGv, REVv, EMITv, PACKv) \
+  k_stream_classify<5, KLv, DBGv, REVv, EMITv, PACKv><<<grid, NH_BLOCK_THREADS, smem, st>>>(db, b, sp)
+  if (b.codes != nullptr) { /* packed input: never with the per-position debug output or per-read runs */
+    if (kl_default) NH_LAUNCH(1, false, false, false, true);
+    else if (db.revcom_version == 0) NH_LAUNCH(0, false, true, false, true);
+    else NH_LAUNCH(0, false, false, false, true);
+  } else if (b.dbg_pos_min != nullptr) /* nh_debug_minimizers (never with emit_runs) */
+    NH_LAUNCH(0, true, false, false, false);
+  else if (kl_default && emit) NH_LAUNCH(1, false, false, true, false);
+  else if (kl_default) NH_LAUNCH(1, false, false, false, false);
+  else if (db.revcom_version == 0 && emit) NH_LAUNCH(0, false, true, true, false);
+  else if (db.revcom_version == 0) NH_LAUNCH(0, false, true, false, false);
+  else if (emit) NH_LAUNCH(0, false, false, true, false);
+  else NH_LAUNCH(0, false, false, false, false);
+#undef NH_LAUNCH
   return 1;
 }
 

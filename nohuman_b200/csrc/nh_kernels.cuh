@@ -15,8 +15,9 @@
 #endif
 #define NH_BLOCK_THREADS (NH_WARPS_PER_BLOCK * 32)
 #define NH_TILE_LMERS 128           /* l-mers per minimizer tile of the warp-per-tile kernel (4 warp iterations) */
-#define NH_FUSED_TILE_POS 508       /* k-mer positions per tile of the lane-serial kernel: 2x300 bp reads stay one tile */
-#define NH_FUSED_TILE_POS_LONG 252  /* ... for batches of long reads: more, smaller groups balance better */
+#define NH_FUSED_TILE_POS 512       /* k-mer positions per tile of the lane-serial kernel: 2x300 bp reads stay one tile */
+#define NH_FUSED_TILE_POS_LONG 256  /* ... for batches of long reads: more, smaller groups balance better
+                                     * (both multiples of 32: tiles of packed input start on a 32-base unit) */
 #define NH_FUSED_TILE_POS_MAX 1023  /* run lengths travel in 10 bits */
 #define NH_MAX_WINDOW 32            /* k - l + 1 must fit one warp */
 #define NH_SMEM_PARENT_MAX 8192     /* taxonomy nodes staged in shared memory */
@@ -102,8 +103,12 @@ struct NhCounters {
 };
 
 struct NhBatchPtrs {
-  const uint8_t *bases;
+  const uint8_t *bases;     /* ASCII, 1 byte per base; null when the batch came packed */
   const uint64_t *offsets;  /* n_seqs + 1 */
+  /* packed input (nh_classify_batch_packed): every sequence starts on a unit of 32 bases */
+  const uint8_t *codes;     /* 2-bit codes, 4 bases per byte, first base in the top bits: 8 bytes per unit */
+  const uint32_t *valid;    /* 1 bit per base, LSB first, 1 = unambiguous base inside the sequence: one word per unit */
+  const uint32_t *poff;     /* n_seqs + 1: first unit of each sequence */
   uint32_t n_seqs;
   uint32_t n_units;
   int32_t paired;

@@ -207,3 +207,42 @@ def test_repeated_minimizers_across_tile_borders(small_db, gpu_db, monkeypatch):
         seqs.append(np.tile(np.frombuffer(b"AC", np.uint8), 250))
     with Session(gpu_db, confidence=0.0) as sess:
         _compare_batch(small_db, sess, seqs, False, 0.0)
+
+
+@pytest.mark.parametrize("mode", ["default", "lane_taxa_1", "tile_pos_96"])
+def test_packed_input_matches_ascii_and_oracle(small_db, gpu_db, mode, monkeypatch):
+    """nh_classify_batch_packed (2-bit codes + validity bits packed on the host): same per-unit call, k-mer
+    total and hit groups as the ASCII entry point and the oracle - ragged lengths, N runs, lower case, junk
+    bytes, multi-tile reads, pairs, and (lane_taxa_1) units that overflow into k_score_big, which then scans
+    the PACKED planes again."""
+    from nohuman_b200 import Session
+    if mode == "lane_taxa_1":
+        monkeypatch.setenv("NH_TEST_LANE_TAXA", "1")
+    if mode == "tile_pos_96":
+        monkeypatch.setenv("NH_FUSED_TILE_POS", "96")
+    rng = np.random.default_rng(23)
+    g = dict(small_db.genomes)
+    seqs = synth.illumina_reads(small_db.genomes, 1200, 150, seed=12, paired=True, n_rate=0.2)
+    seqs += synth.ont_reads(small_db.genomes, 40, seed=6, n50=3000, max_len=20000)
+    for L in [0, 1, 31, 32, 33, 34, 35, 36, 63, 64, 65, 511, 512, 513, 545, 546, 547, 1057, 1058, 16418, 16419]:
+        o = int(rng.integers(0, len(g[9606]) - L - 1))
+        seqs.append(g[9606][o:o + L].copy())
+    r = g[562][500:1400].copy(); r[100:140] = ord("N"); r[300] = ord("n"); r[400:600] |= 0x20; r[700] = 0; seqs.append(r)
+    for i in range(60):  # chimeras: several taxa per unit
+        seqs.append(np.concatenate([g[9606][i * 40:i * 40 + 75], g[562][i * 30:i * 30 + 75], g[1423][i * 20:i * 20 + 90]]))
+    if len(seqs) % 2:
+        seqs.append(seqs[-1][:100].copy())
+    bases, offsets = synth.pack(seqs)
+    for paired, conf in ((True, 0.1), (False, 0.0)):
+        small_db.confidence = conf
+        want = small_db.classify_batch(bases, offsets, paired=paired)
+        with Session(gpu_db, confidence=conf, paired=paired, max_batch_bases=len(bases) + 4096) as sess:
+            call, keep, st = sess.classify_packed(bases, offsets, threads=3)
+            icall, tk, hg = sess.debug_last_batch(len(call))
+            call_a, keep_a, _ = sess.classify(bases, offsets)
+        np.testing.assert_array_equal(tk, want["total_kmers"])
+        np.testing.assert_array_equal(hg, want["hit_groups"])
+        np.testing.assert_array_equal(call, want["ext"])
+        np.testing.assert_array_equal(call, call_a)
+        np.testing.assert_array_equal(keep, keep_a)
+        assert st.fused_kernel == 2

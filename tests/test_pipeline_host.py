@@ -368,3 +368,47 @@ def test_long_reads_cut_chunks_by_bases_and_mates_stay_together(tmp_path):
     assert st.total == n
     assert open(o1, "rb").read() == expected(r1, keep, call)
     assert open(o2, "rb").read() == expected(r2, keep, call)
+
+
+def test_pack_reads_matches_the_scalar_definition():
+    """nh_pack_reads (host, AVX2 when available): 2-bit codes with the first base in the top bits, validity bits LSB
+    first, every sequence on a unit of 32 bases, padding invalid; the same for 1 and many threads."""
+    from nohuman_b200.api import pack_reads, packed_units
+    rng = np.random.default_rng(1)
+    lens = np.concatenate([rng.integers(0, 300, size=3000), [0, 1, 31, 32, 33, 64, 4097]])
+    off = np.zeros(len(lens) + 1, np.uint64)
+    off[1:] = np.cumsum(lens)
+    alpha = np.frombuffer(b"ACGTacgtNnRY\x00-", np.uint8)
+    p = np.array([.2, .2, .2, .2, .03, .03, .03, .03, .02, .01, .01, .01, .005, .005])
+    bases = alpha[rng.choice(len(alpha), size=int(off[-1]), p=p / p.sum())]
+    code_of = np.full(256, 255, np.uint8)
+    for i, ch in enumerate(b"ACGT"):
+        code_of[ch] = code_of[ch | 0x20] = i
+    units = (lens + 31) // 32
+    want_poff = np.zeros(len(lens) + 1, np.uint32)
+    want_poff[1:] = np.cumsum(units)
+    assert packed_units(off) == int(units.sum())
+    ref = None
+    for thr in (1, 5):
+        codes, valid, poff = pack_reads(bases, off, thr)
+        np.testing.assert_array_equal(poff, want_poff)
+        # unpack everything back to per-base (code, valid) and compare with the definition
+        nu = int(units.sum())
+        c4 = codes[:nu * 8]
+        per_base_code = np.stack([(c4 >> 6) & 3, (c4 >> 4) & 3, (c4 >> 2) & 3, c4 & 3], axis=1).reshape(-1)
+        per_base_valid = ((valid[:nu, None] >> np.arange(32, dtype=np.uint32)[None, :]) & 1).reshape(-1).astype(bool)
+        for s in (0, 1, 17, 2999, len(lens) - 1, len(lens) - 3):
+            pass
+        pos = np.concatenate([np.arange(int(want_poff[s]) * 32, int(want_poff[s]) * 32 + int(lens[s])) for s in range(len(lens))])
+        want_code = code_of[bases]
+        ok = want_code != 255
+        np.testing.assert_array_equal(per_base_valid[pos], ok)
+        np.testing.assert_array_equal(per_base_code[pos][ok], want_code[ok])
+        inside = np.zeros(nu * 32, bool)
+        inside[pos] = True
+        assert not per_base_valid[~inside].any()  # padding is invalid
+        if ref is None:
+            ref = (codes.copy(), valid.copy())
+        else:
+            np.testing.assert_array_equal(codes, ref[0])
+            np.testing.assert_array_equal(valid, ref[1])
