@@ -118,7 +118,7 @@ def test_edge_cases(small_db, gpu_db):
         _compare_batch(small_db, sess, pseqs, True, 0.2)
 
 
-@pytest.mark.parametrize("mode", ["legacy", "lane_taxa_1", "lane_taxa_2", "tile_pos_60", "tile_pos_252", "tile_pos_1023"])
+@pytest.mark.parametrize("mode", ["legacy", "lane_taxa_1", "lane_taxa_2", "tile_pos_60", "tile_pos_256", "tile_pos_1023"])
 def test_kernel_path_variants_match_oracle(small_db, gpu_db, mode, monkeypatch):
     """The warp-per-tile kernels (NH_LEGACY_KERNELS=1), the streaming kernel with a shrunken
     in-warp taxon table (units overflow into k_score_big, which classifies them again from
@@ -148,7 +148,7 @@ def test_kernel_path_variants_match_oracle(small_db, gpu_db, mode, monkeypatch):
     assert len(set(want["call"].tolist())) > 4
 
 
-@pytest.mark.parametrize("tile_pos", [508, 252, 100])
+@pytest.mark.parametrize("tile_pos", [512, 256, 100])
 def test_lengths_straddling_tile_and_group_borders(small_db, gpu_db, tile_pos, monkeypatch):
     """Reads whose k-mer positions end exactly at, one before and one after a tile border, units of
     2..33 tiles (scored in the warp when all tiles share a group of 32, by k_score otherwise), and
