@@ -454,7 +454,7 @@ def main():
                     continue
                 ipc = max(16, 4096 // (bps * depth))  # every launch issues ~150 M requests: 4-5 ms
                 items_s, req_s = db.probe_pattern(lanes=lanes, p_continue=p, sm_window_bytes=win, items_per_chain=ipc,
-                                                  iters=2, depth=depth, blocks_per_sm=bps)
+                                                  iters=4, depth=depth, blocks_per_sm=bps)
                 if best is None or items_s > best[0]:
                     best = (items_s, req_s, bps, depth)
             variants.append({"pattern": name, "lanes": lanes, "p_continue": round(p, 4), "sm_window_bytes": win,
