@@ -10,7 +10,6 @@
 #include <stdint.h>
 #include <string.h>
 
-#include <atomic>
 #include <thread>
 #include <vector>
 
@@ -100,7 +99,6 @@ extern "C" int nh_pack_reads(const uint8_t *bases, const uint64_t *offsets, uint
    * starts, writes poff and packs */
   std::vector<uint64_t> part((size_t)threads + 1, 0);
   std::vector<std::thread> th;
-  std::atomic<int> overflow{0};
   auto range = [&](int t, uint64_t *a, uint64_t *b) {
     *a = n_seqs * (uint64_t)t / (uint64_t)threads;
     *b = n_seqs * (uint64_t)(t + 1) / (uint64_t)threads;
@@ -129,6 +127,5 @@ extern "C" int nh_pack_reads(const uint8_t *bases, const uint64_t *offsets, uint
     });
   for (auto &x : th) x.join();
   poff[n_seqs] = (uint32_t)part[(size_t)threads];
-  (void)overflow;
   return NH_OK;
 }

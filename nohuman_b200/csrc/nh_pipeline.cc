@@ -77,7 +77,6 @@ struct StageClock {
     for (auto &x : ns) x = 0;
   }
 };
-static thread_local StageClock *t_clock = nullptr; /* set by every pipeline thread */
 struct Busy {
   StageClock *c;
   int st;
@@ -1499,7 +1498,8 @@ static int run_pipeline(const Decider &dec, const nh_files_t *files, nh_run_stat
             uint64_t u0 = 0, runs_at = 0;
             while (w->error.empty() && u0 < w->n_units) {
               uint64_t o = 0, s = 0, u1 = u0;
-              Busy *staging = new Busy(&clock, ST_STAGE);
+              {
+              Busy staging(&clock, ST_STAGE);
               for (; u1 < w->n_units; u1++) {
                 uint64_t ub = 0;
                 for (int f = 0; f < nf; f++) ub += w->c[f].recs[u1].seq_len;
@@ -1512,7 +1512,7 @@ static int run_pipeline(const Decider &dec, const nh_files_t *files, nh_run_stat
                 }
               }
               h_off[s] = o;
-              delete staging;
+              }
               Busy classifying(&clock, ST_CLASSIFY);
               if (nh_classify_batch(sess, h_bases, h_off, s, w->call.data() + u0, w->keep.data() + u0, nullptr) != NH_OK)
                 w->error = std::string("classification failed: ") + nh_last_error();
