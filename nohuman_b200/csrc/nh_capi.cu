@@ -666,6 +666,7 @@ int nh_session_create_ex(nh_db *db, const nh_params_t *params, bool need_lookups
   ALLOC(s->d_bases, mb + 64);
   ALLOC(s->d_offsets, ms + 1);
   ALLOC(s->d_tile_base, ms + 2);
+  ALLOC(s->d_seq_info, ms + 1);
   ALLOC(s->d_block_sums, ms / 1024 + 2);
   ALLOC(s->d_tiles, s->cap_tiles);
   ALLOC(s->d_tile_out, s->cap_tiles);
@@ -722,6 +723,7 @@ extern "C" void nh_session_destroy(nh_session *s) {
   cudaFree(s->d_bases);
   cudaFree(s->d_offsets);
   cudaFree(s->d_tile_base);
+  cudaFree(s->d_seq_info);
   cudaFree(s->d_block_sums);
   cudaFree(s->d_tiles);
   cudaFree(s->d_tile_out);
@@ -828,6 +830,9 @@ static int enqueue_batch(nh_session *s, const uint8_t *d_bases, const uint64_t *
   B.deferred_units = fused ? s->d_deferred : nullptr;
   const bool emit = s->params.emit_runs && d_pos_min == nullptr;
   B.emit_all_taxa = emit ? 1 : 0;
+  /* batches of long reads (more than 4 tiles per sequence on average): descriptors written per tile */
+  B.tiles_upper = (uint32_t)tiles_upper;
+  B.seq_info = tiles_upper > 4 * n_seqs ? s->d_seq_info : nullptr;
   launches += nh_launch_plan(P, B, st);
   cudaEventRecord(s->ev[EV_MIN0], st);
   if (fused) {

@@ -45,6 +45,7 @@ struct nh_session {
   uint8_t *d_bases = nullptr;
   uint64_t *d_offsets = nullptr;
   uint32_t *d_tile_base = nullptr;
+  uint2 *d_seq_info = nullptr;
   uint64_t *d_block_sums = nullptr;
   NhTile *d_tiles = nullptr;
   NhTileOut *d_tile_out = nullptr;

@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(PLAN_THREADS)
 k_plan_fill(const uint64_t *__restrict__ off, uint32_t n_seqs, int k, int tile_pos, int paired,
             int fused, const uint64_t *__restrict__ block_sums, uint32_t *__restrict__ tile_base,
             NhTile *__restrict__ tiles, uint32_t *__restrict__ deferred_units,
-            NhCounters *__restrict__ counters) {
+            NhCounters *__restrict__ counters, uint2 *__restrict__ seq_info) {
   __shared__ uint64_t s_warp[33];
   uint32_t s = blockIdx.x * PLAN_THREADS + threadIdx.x;
   uint64_t w = s < n_seqs ? seq_work(off, s, k, tile_pos) : 0;
@@ -164,17 +164,45 @@ k_plan_fill(const uint64_t *__restrict__ off, uint32_t n_seqs, int k, int tile_p
       if (mate == 0u && !in_warp) /* also units without any k-mer: k_score calls them unclassified */
         deferred_units[atomicAdd(&counters->n_deferred, 1u)] = paired ? (s >> 1) : s;
     }
-    for (uint32_t t = 0; t < v; t++) {
-      NhTile d;
-      d.seq = s;
-      d.pos_begin = t * (uint32_t)tile_pos;
-      d.slot = pb + d.pos_begin;
-      d.role = !in_warp ? NH_ROLE_DEFERRED
-                        : (tb + t == first_tile ? NH_ROLE_LEADER : (NH_ROLE_MEMBER | ((tb + t - first_tile) << 8)));
-      tiles[tb + t] = d;
+    if (seq_info != nullptr) {
+      /* long reads: k_plan_tiles writes the descriptors, one thread per tile */
+      seq_info[s] = make_uint2(pb, in_warp ? first_tile : 0xFFFFFFFFu);
+    } else {
+      for (uint32_t t = 0; t < v; t++) {
+        NhTile d;
+        d.seq = s;
+        d.pos_begin = t * (uint32_t)tile_pos;
+        d.slot = pb + d.pos_begin;
+        d.role = !in_warp ? NH_ROLE_DEFERRED
+                          : (tb + t == first_tile ? NH_ROLE_LEADER : (NH_ROLE_MEMBER | ((tb + t - first_tile) << 8)));
+        tiles[tb + t] = d;
+      }
     }
   }
   if (s == 0) tile_base[n_seqs] = counters->n_tiles;
+}
+
+/* The tile descriptors of a batch of long reads, one thread per tile (a 100 kb read has 400 tiles:
+ * one thread writing them all was 7 % of a step of 50 kb reads).  The sequence of a tile is found
+ * by bisection over tile_base. */
+__global__ void __launch_bounds__(256)
+k_plan_tiles(const uint32_t *__restrict__ tile_base, const uint2 *__restrict__ seq_info, uint32_t n_seqs, int tile_pos,
+             NhTile *__restrict__ tiles, const NhCounters *__restrict__ counters) {
+  const uint32_t n_tiles = counters->n_tiles;
+  for (uint32_t tile = blockIdx.x * blockDim.x + threadIdx.x; tile < n_tiles; tile += gridDim.x * blockDim.x) {
+    uint32_t lo = 0, hi = n_seqs; /* last s with tile_base[s] <= tile (sequences without tiles share their successor's base) */
+    while (hi - lo > 1u) {
+      const uint32_t mid = (lo + hi) >> 1;
+      if (tile_base[mid] <= tile) lo = mid; else hi = mid;
+    }
+    const uint2 si = seq_info[lo];
+    NhTile d;
+    d.seq = lo;
+    d.pos_begin = (tile - tile_base[lo]) * (uint32_t)tile_pos;
+    d.slot = si.x + d.pos_begin;
+    d.role = si.y == 0xFFFFFFFFu ? NH_ROLE_DEFERRED : (tile == si.y ? NH_ROLE_LEADER : (NH_ROLE_MEMBER | ((tile - si.y) << 8)));
+    tiles[tile] = d;
+  }
 }
 
 /* ------------------------------------------------------------------ */
@@ -1591,8 +1619,12 @@ int nh_launch_plan(const NhDbParams &db, const NhBatchPtrs &b, cudaStream_t st) 
   k_plan_scan<<<1, PLAN_THREADS, 0, st>>>(b.block_sums, nb, b.counters);
   k_plan_fill<<<nb, PLAN_THREADS, 0, st>>>(b.offsets, b.n_seqs, db.k, db.tile_pos, b.paired,
                                            b.deferred_units != nullptr, b.block_sums, b.tile_base,
-                                           b.tiles, b.deferred_units, b.counters);
-  return 3;
+                                           b.tiles, b.deferred_units, b.counters, b.seq_info);
+  if (b.seq_info == nullptr) return 3;
+  uint32_t blocks = (b.tiles_upper + 255u) / 256u;
+  if (blocks > 148u * 16u) blocks = 148u * 16u;
+  k_plan_tiles<<<blocks ? blocks : 1u, 256, 0, st>>>(b.tile_base, b.seq_info, b.n_seqs, db.tile_pos, b.tiles, b.counters);
+  return 4;
 }
 
 bool nh_fused_supported(const NhDbParams &db) {

@@ -114,6 +114,8 @@ struct NhBatchPtrs {
   int32_t paired;
   /* plan */
   uint32_t *tile_base;      /* n_seqs + 1: first tile of each sequence */
+  uint2 *seq_info;          /* null, or (batches of long reads) per sequence: lookup slot base, first tile of its in-warp unit */
+  uint32_t tiles_upper;     /* host-side bound on the number of tiles */
   uint64_t *block_sums;
   NhTile *tiles;
   NhTileOut *tile_out;
