@@ -66,6 +66,8 @@ def parse_args():
     ap.add_argument("--workload-mbases", type=int, default=150, help="bases per GPU of each `workloads` entry")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-packed", default="6x6,8x4,4x8", help="packed e2e shapes 'workers x pack threads' (0 = cores / workers), "
+                    "comma separated; the best one is reported, all are listed")
     ap.add_argument("--no-workloads", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
     return ap.parse_args()
@@ -616,13 +618,17 @@ def run_e2e(args, torch, dist, db, bufs, d_off, n_pairs, n_seqs, total, world, s
     H2D and its calls + keep mask D2H.  Two sessions on two host threads overlap one launch's copies with the
     other's kernel.  A step is again launches_per_step launches.
 
-    Two input formats: "ascii" = nh_classify_batch (1 byte per base over PCIe); "packed" = nh_pack_reads on the
-    host cores INSIDE the timed region (ASCII -> 2-bit codes + validity bits, 0.4 byte per base) followed by
-    nh_classify_batch_packed.  Packing is host-DRAM bound, so it only pays while one process has the host to
-    itself: measured at N = 1, reported next to the ASCII number, and `e2e` is the better of the two."""
-    import ctypes as C
-    from nohuman_b200 import Session, _ffi
-    n_workers = 2
+    Two transfer formats for the same ASCII host buffers: "ascii" = nh_classify_batch (1 byte per base over
+    PCIe, no host core involved); "packed" = nh_classify_batch_pack (the host cores pack INSIDE the timed region,
+    0.48 byte per base crosses PCIe), run with several sessions on as many host threads so that the cores keep
+    packing while other sessions' copies and kernels run.  Packing needs the host's cores and memory bandwidth,
+    so it is measured at N = 1 only (one process per host); `e2e` is the better of the two."""
+    from nohuman_b200 import Session
+    shapes = []
+    for item in args.e2e_packed.split(","):
+        w, t = item.lower().split("x")
+        shapes.append((max(1, int(w)), int(t) if int(t) > 0 else max(1, (os.cpu_count() or 2) // max(1, int(w)))))
+    n_workers = max([2] + [w for w, _ in shapes]) if world == 1 else 2
     n_host = min(4, len(bufs))  # distinct pinned host batches (1.3 GB), cycled
     sessions = [Session(db, confidence=CONF, paired=True, max_batch_bases=total + 4096,
                         max_batch_seqs=n_seqs) for _ in range(n_workers)]
@@ -636,37 +642,32 @@ def run_e2e(args, torch, dist, db, bufs, d_off, n_pairs, n_seqs, total, world, s
     outs = [(torch.empty(n_pairs, dtype=torch.int32).pin_memory(), torch.empty(n_pairs, dtype=torch.uint8).pin_memory())
             for _ in range(n_workers)]
     units = n_seqs * ((READ_LEN + 31) // 32)
-    packed = [(torch.empty(units * 8 + 64, dtype=torch.uint8).pin_memory(), torch.empty(units + 16, dtype=torch.int32).pin_memory(),
-               torch.empty(n_seqs + 1, dtype=torch.int32).pin_memory()) for _ in range(n_workers)]
     torch.cuda.synchronize()
     n_launch = args.launches_per_step
     steps = args.steps
-    pack_threads = max(1, (os.cpu_count() or 2) // n_workers)
-    L = _ffi.lib()
+    cur = {"workers": 2, "pack_threads": max(1, (os.cpu_count() or 2) // 2)}
 
     def worker(fmt, w, n):
         hc, hk = outs[w]
-        pc, pv, pp = packed[w]
+        nw, pack_threads = cur["workers"], cur["pack_threads"]
         for i in range(n):
-            hb = host[(w + n_workers * i) % n_host]
+            hb = host[(w + nw * i) % n_host]
             if fmt == "ascii":
                 sessions[w].classify_raw(hb.data_ptr(), ho.data_ptr(), n_seqs, hc.data_ptr(), hk.data_ptr())
             else:
-                _ffi.check(L.nh_pack_reads(hb.data_ptr(), ho.data_ptr(), n_seqs, pc.data_ptr(), pv.data_ptr(), pp.data_ptr(),
-                                           pack_threads))
-                sessions[w].classify_packed_raw(pc.data_ptr(), pv.data_ptr(), pp.data_ptr(), ho.data_ptr(), n_seqs,
-                                                hc.data_ptr(), hk.data_ptr())
+                sessions[w].classify_pack_raw(hb.data_ptr(), ho.data_ptr(), n_seqs, pack_threads, hc.data_ptr(), hk.data_ptr())
 
     def run(fmt, n_total):
-        ths = [threading.Thread(target=worker, args=(fmt, w, n_total // n_workers + (1 if w < n_total % n_workers else 0)))
-               for w in range(n_workers)]
+        nw = cur["workers"]
+        ths = [threading.Thread(target=worker, args=(fmt, w, n_total // nw + (1 if w < n_total % nw else 0)))
+               for w in range(nw)]
         for t in ths:
             t.start()
         for t in ths:
             t.join()
 
     def timed(fmt):
-        run(fmt, max(args.warmup, 1) * n_workers * 2)
+        run(fmt, max(args.warmup, 1) * cur["workers"] * 2)
         if dist:
             dist.barrier()
         torch.cuda.synchronize()
@@ -692,20 +693,33 @@ def run_e2e(args, torch, dist, db, bufs, d_off, n_pairs, n_seqs, total, world, s
     formats = {"ascii": res_a}
     best = res_a
     if world == 1:
-        res_p, calls_p = timed("packed")
-        res_p["input_format"] = (f"packed on the host inside the timed region ({pack_threads} threads per session thread, nh_pack_reads) "
-                                 "-> 2-bit codes + validity bits, 0.4 byte per base (nh_classify_batch_packed)")
-        res_p["same_calls_as_ascii"] = bool(torch.equal(calls_a, calls_p))
+        # nh_classify_batch_pack at several thread shapes (session threads x packing threads per session);
+        # the best one that reproduces the ASCII calls counts
+        res_p, sweep = None, []
+        for nw, pt in shapes:
+            cur["workers"], cur["pack_threads"] = nw, pt
+            r, calls_p = timed("packed")
+            r["session_threads"], r["pack_threads_per_session_thread"] = nw, pt
+            r["same_calls_as_ascii"] = bool(torch.equal(calls_a, calls_p))
+            sweep.append({"session_threads": nw, "pack_threads": pt, "value": r["value"]})
+            if res_p is None or (r["same_calls_as_ascii"] and r["value"] > res_p["value"]):
+                res_p = r
+        res_p["input_format"] = ("ASCII host buffers handed to nh_classify_batch_pack: packed by the host cores INSIDE the timed region "
+                                 "(AVX2, 2-bit codes + validity bits), 0.48 byte per base over PCIe")
+        if len(sweep) > 1:
+            res_p["shapes_tried"] = sweep
         formats["packed"] = res_p
         if res_p["value"] > best["value"] and res_p["same_calls_as_ascii"]:
             best = res_p
+        cur["workers"] = 2
     for s in sessions:
         s.close()
     out = dict(best)
-    out["api"] = f"host buffers (pinned ASCII), 2 sessions on 2 host threads, {n_host} distinct host batches cycled"
+    out["api"] = (f"host buffers (pinned ASCII), {best.get('session_threads', 2)} sessions on as many host threads, "
+                  f"{n_host} distinct host batches cycled")
     out["formats"] = formats
-    out["note"] = ("packing is bound by host DRAM (tools/pack_bench.cc: 73 Gbases/s on 16 cores, 103 on 32) while one PCIe link moves "
-                   "52 Gbases/s of ASCII without using a core; with more than one rank per host the ASCII path is used (DESIGN.md §4c)")
+    out["note"] = ("packing costs host cores (tools/pack_bench.cc: 8 Gbases/s per core, 86-103 on 16) while one PCIe link moves 52 Gbases/s "
+                   "of ASCII without using a core; with more than one rank per host the ASCII path is measured (DESIGN.md §4c)")
     return out
 
 

@@ -178,6 +178,13 @@ int nh_pack_reads(const uint8_t *bases, const uint64_t *offsets, uint64_t n_seqs
 int nh_classify_batch_packed(nh_session *s, const uint8_t *codes, const uint32_t *valid, const uint32_t *poff,
                              const uint64_t *offsets, uint64_t n_seqs, uint32_t *out_call, uint8_t *out_keep,
                              nh_batch_stats_t *stats);
+/* nh_classify_batch (same arguments, same results: ASCII bases in host memory) with the transfer done in the
+ * packed format: nh_pack_reads + nh_classify_batch_packed in one call.  A pool of `pack_threads` threads owned by
+ * the session packs into the session's pinned planes; the calling thread sleeps (it does not spin) until the
+ * results are back, so that several sessions on several host threads keep every core packing while the other
+ * sessions' copies and kernels run — how bench.py's `e2e` gets 76-84 Gbp/s out of a PCIe link that moves 52 GB/s. */
+int nh_classify_batch_pack(nh_session *s, const uint8_t *bases, const uint64_t *offsets, uint64_t n_seqs,
+                           int pack_threads, uint32_t *out_call, uint8_t *out_keep, nh_batch_stats_t *stats);
 
 /* Same with DEVICE-resident input and output (all pointers are device
  * pointers on the session's device; d_bases must be 16-byte aligned, as any

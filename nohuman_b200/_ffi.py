@@ -105,6 +105,7 @@ SYMBOLS = {
     "nh_packed_units": (_i32, [_vp, _u64, C.POINTER(_u64)]),
     "nh_pack_reads": (_i32, [_vp, _vp, _u64, _vp, _vp, _vp, _i32]),
     "nh_classify_batch_packed": (_i32, [_vp, _vp, _vp, _vp, _vp, _u64, _vp, _vp, C.POINTER(BatchStats)]),
+    "nh_classify_batch_pack": (_i32, [_vp, _vp, _vp, _u64, _i32, _vp, _vp, C.POINTER(BatchStats)]),
     "nh_session_sync": (_i32, [_vp, C.POINTER(BatchStats)]),
     "nh_run_files": (_i32, [_vp, C.POINTER(Files), C.POINTER(RunStats)]),
     "nh_run_files_multi": (_i32, [C.POINTER(_vp), _i32, C.POINTER(Files), C.POINTER(RunStats)]),

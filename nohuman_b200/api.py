@@ -223,6 +223,27 @@ class Session:
                                              keep_ptr, C.byref(st)))
         return st
 
+    def classify_pack(self, bases: np.ndarray, offsets: np.ndarray, threads: int = 1):
+        """nh_classify_batch_pack: ASCII in, packed by the session's pool of `threads` host threads into
+        pinned planes, sent in the packed format; same results as classify()."""
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        n_seqs = len(offsets) - 1
+        n_units = n_seqs // 2 if self.paired else n_seqs
+        call = np.zeros(n_units, np.uint32)
+        keep = np.zeros(n_units, np.uint8)
+        st = BatchStats()
+        check(lib().nh_classify_batch_pack(self._h, bases.ctypes.data, offsets.ctypes.data, n_seqs, int(threads),
+                                           call.ctypes.data, keep.ctypes.data, C.byref(st)))
+        return call, keep, st
+
+    def classify_pack_raw(self, bases_ptr: int, offsets_ptr: int, n_seqs: int, threads: int, call_ptr: int,
+                          keep_ptr: int) -> BatchStats:
+        st = BatchStats()
+        check(lib().nh_classify_batch_pack(self._h, bases_ptr, offsets_ptr, n_seqs, int(threads), call_ptr, keep_ptr,
+                                           C.byref(st)))
+        return st
+
     # -- device-resident (asynchronous on the session stream) ---------
     def classify_device(self, d_bases: int, d_offsets: int, n_seqs: int, total_bases: int,
                         d_out_call: int, d_out_keep: int) -> None:

@@ -15,7 +15,11 @@
 #include <sys/stat.h>
 
 #include <algorithm>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/nohuman_gpu.h"
@@ -747,6 +751,11 @@ extern "C" void nh_session_destroy(nh_session *s) {
   cudaFree(s->d_codes);
   cudaFree(s->d_valid);
   cudaFree(s->d_poff);
+  nh_pack_pool_destroy(s->pack_pool); /* joins the packer threads */
+  if (s->h_codes) cudaFreeHost(s->h_codes);
+  if (s->h_valid) cudaFreeHost(s->h_valid);
+  if (s->h_poff) cudaFreeHost(s->h_poff);
+  if (s->ev_block) cudaEventDestroy(s->ev_block);
   if (s->h_counters) cudaFreeHost(s->h_counters);
   for (int i = 0; i < NH_NUM_EVENTS; i++)
     if (s->ev[i]) cudaEventDestroy(s->ev[i]);
@@ -960,6 +969,16 @@ extern "C" int nh_classify_batch(nh_session *s, const uint8_t *bases, const uint
   return nh_session_sync(s, stats);
 }
 
+static int ensure_packed_planes(nh_session *s, uint64_t cap_units) {
+  if (s->d_codes) return NH_OK; /* allocated on the first packed batch */
+  cudaError_t e = cudaMalloc(&s->d_codes, cap_units * 8 + 64);
+  if (e == cudaSuccess) e = cudaMalloc(&s->d_valid, cap_units * 4 + 64);
+  if (e == cudaSuccess) e = cudaMalloc(&s->d_poff, (s->cap_seqs + 1) * 4);
+  if (e != cudaSuccess) return nh_set_error(NH_ERR_NOMEM, "allocating the packed input planes failed: %s", cudaGetErrorString(e));
+  s->device_bytes += cap_units * 12 + 128 + (s->cap_seqs + 1) * 4;
+  return NH_OK;
+}
+
 /* Packed host input: 2-bit codes + validity bits + unit offsets (nh_pack_reads) instead of ASCII.
  * 0.4 bytes per base cross PCIe; the kernel instantiation that reads the planes also skips the
  * ASCII -> 2-bit step. */
@@ -983,13 +1002,8 @@ extern "C" int nh_classify_batch_packed(nh_session *s, const uint8_t *codes, con
   const uint64_t units = poff[n_seqs];
   const uint64_t cap_units = s->cap_bases / 32 + s->cap_seqs + 1;
   if (units > cap_units) return nh_set_error(NH_ERR_CAPACITY, "packed batch has %llu units, session holds %llu", (unsigned long long)units, (unsigned long long)cap_units);
-  if (!s->d_codes) { /* allocated on the first packed batch */
-    cudaError_t e = cudaMalloc(&s->d_codes, cap_units * 8 + 64);
-    if (e == cudaSuccess) e = cudaMalloc(&s->d_valid, cap_units * 4 + 64);
-    if (e == cudaSuccess) e = cudaMalloc(&s->d_poff, (s->cap_seqs + 1) * 4);
-    if (e != cudaSuccess) return nh_set_error(NH_ERR_NOMEM, "allocating the packed input planes failed: %s", cudaGetErrorString(e));
-    s->device_bytes += cap_units * 12 + 128 + (s->cap_seqs + 1) * 4;
-  }
+  rc = ensure_packed_planes(s, cap_units);
+  if (rc) return rc;
   cudaStream_t st = s->stream;
   const uint64_t n_units = s->params.paired ? n_seqs / 2 : n_seqs;
   cudaEventRecord(s->ev[EV_H2D0], st);
@@ -1007,11 +1021,133 @@ extern "C" int nh_classify_batch_packed(nh_session *s, const uint8_t *codes, con
   if (out_keep) CUDA_TRY(cudaMemcpyAsync(out_keep, s->d_out_keep, n_units, cudaMemcpyDeviceToHost, st));
   cudaEventRecord(s->ev[EV_D2H1], st);
   s->timed_copies = true;
+  /* sleep until the results are back instead of spinning: callers of the packed entry points run several
+   * sessions on host threads whose cores are busy packing the next batches */
+  if (!s->ev_block) CUDA_TRY(cudaEventCreateWithFlags(&s->ev_block, cudaEventDisableTiming | cudaEventBlockingSync));
+  CUDA_TRY(cudaEventRecord(s->ev_block, st));
+  CUDA_TRY(cudaEventSynchronize(s->ev_block));
   return nh_session_sync(s, stats);
 }
 
 /* ------------------------------------------------------------------ */
 /* per-stage entry points for the parity tests                          */
+
+/* ---- nh_classify_batch_pack: ASCII host input, sent in the packed format ----
+ * nh_pack_reads + nh_classify_batch_packed in one call: a pool of `pack_threads` packer threads that lives with
+ * the session fills the session's own pinned planes (non-temporal stores: the next reader is the copy engine),
+ * three large copies follow, and the calling thread sleeps until the results are back.  Several sessions on as
+ * many host threads keep the cores packing while other sessions' copies and kernels run (bench.py `e2e`).
+ * A finer-grained pipeline — chunks packed into a ring of cache-resident staging slots and copied one by one —
+ * was built and measured slower (56-66 against 76-84 Gbp/s): with every core streaming reads, copies out of the
+ * slots ran at 34 GB/s instead of 52. */
+struct NhPackPool {
+  std::vector<std::thread> threads;
+  std::mutex mu;
+  std::condition_variable cv_job, cv_done;
+  uint64_t generation = 0;
+  int running = 0;
+  bool quit = false;
+  std::function<void(int)> job;
+
+  explicit NhPackPool(int n) {
+    for (int t = 0; t < n; t++)
+      threads.emplace_back([this, t] {
+        uint64_t seen = 0;
+        for (;;) {
+          std::function<void(int)> fn;
+          {
+            std::unique_lock<std::mutex> lk(mu);
+            cv_job.wait(lk, [&] { return quit || generation != seen; });
+            if (quit) return;
+            seen = generation;
+            fn = job;
+          }
+          fn(t);
+          {
+            std::lock_guard<std::mutex> lk(mu);
+            if (--running == 0) cv_done.notify_all();
+          }
+        }
+      });
+  }
+  void run(std::function<void(int)> fn) { /* on every thread of the pool; returns when all are done */
+    std::unique_lock<std::mutex> lk(mu);
+    job = std::move(fn);
+    running = (int)threads.size();
+    generation++;
+    cv_job.notify_all();
+    cv_done.wait(lk, [&] { return running == 0; });
+  }
+  ~NhPackPool() {
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      quit = true;
+    }
+    cv_job.notify_all();
+    for (auto &t : threads) t.join();
+  }
+};
+
+void nh_pack_pool_destroy(NhPackPool *p) { delete p; }
+
+extern "C" int nh_classify_batch_pack(nh_session *s, const uint8_t *bases, const uint64_t *offsets, uint64_t n_seqs,
+                                      int pack_threads, uint32_t *out_call, uint8_t *out_keep, nh_batch_stats_t *stats) {
+  if (!s || !offsets || (!bases && n_seqs && offsets[n_seqs] > 0)) return nh_set_error(NH_ERR_INVALID, "null argument");
+  if (!s->use_fused) return nh_set_error(NH_ERR_UNSUPPORTED, "packed input needs the streaming kernel (window of 5 l-mers)");
+  if (s->params.emit_runs) return nh_set_error(NH_ERR_UNSUPPORTED, "packed input is not available to sessions created with emit_runs");
+  const uint64_t total = n_seqs ? offsets[n_seqs] - offsets[0] : 0;
+  if (n_seqs && offsets[0] != 0) return nh_set_error(NH_ERR_INVALID, "offsets[0] must be 0");
+  int rc = check_batch_args(s, n_seqs, total);
+  if (rc) return rc;
+  CUDA_TRY(cudaSetDevice(s->db->info.device));
+  if (n_seqs == 0) {
+    s->pending = false;
+    if (stats) memset(stats, 0, sizeof *stats);
+    return NH_OK;
+  }
+  const uint64_t cap_units = s->cap_bases / 32 + s->cap_seqs + 1;
+  const int T = pack_threads < 1 ? 1 : pack_threads > 256 ? 256 : pack_threads;
+  if (!s->pack_pool || s->pack_threads != T) {
+    nh_pack_pool_destroy(s->pack_pool);
+    s->pack_pool = new NhPackPool(T);
+    s->pack_threads = T;
+  }
+  if (!s->h_codes) { /* pinned planes for a whole batch, allocated on the first call */
+    cudaError_t e = cudaMallocHost(&s->h_codes, cap_units * 8 + 64);
+    if (e == cudaSuccess) e = cudaMallocHost(&s->h_valid, cap_units * 4 + 64);
+    if (e == cudaSuccess) e = cudaMallocHost(&s->h_poff, (s->cap_seqs + 1) * 4);
+    if (e != cudaSuccess) return nh_set_error(NH_ERR_NOMEM, "pinned planes for the packed batch: %s", cudaGetErrorString(e));
+  }
+  /* units per thread range; prefix over the ranges; unit offsets and the planes of every range */
+  std::vector<uint64_t> part((size_t)T + 1, 0);
+  auto range = [&](int t, uint64_t *a, uint64_t *b) {
+    *a = n_seqs * (uint64_t)t / (uint64_t)T;
+    *b = n_seqs * (uint64_t)(t + 1) / (uint64_t)T;
+  };
+  s->pack_pool->run([&](int t) {
+    uint64_t a, b, u = 0;
+    range(t, &a, &b);
+    for (uint64_t q = a; q < b; q++) u += (offsets[q + 1] - offsets[q] + 31) >> 5;
+    part[(size_t)t + 1] = u;
+  });
+  for (int t = 0; t < T; t++) part[(size_t)t + 1] += part[(size_t)t];
+  const uint64_t units = part[(size_t)T];
+  if (units > cap_units || units > 0xFFFFFFFFull)
+    return nh_set_error(NH_ERR_CAPACITY, "packed batch has %llu units, session holds %llu", (unsigned long long)units, (unsigned long long)cap_units);
+  uint32_t *h_poff = s->h_poff;
+  s->pack_pool->run([&](int t) {
+    uint64_t a, b;
+    range(t, &a, &b);
+    uint64_t u = part[(size_t)t];
+    for (uint64_t q = a; q < b; q++) {
+      h_poff[q] = (uint32_t)u;
+      u += (offsets[q + 1] - offsets[q] + 31) >> 5;
+    }
+    nh_pack_range(bases, offsets, total, a, b, s->h_codes, s->h_valid, h_poff);
+  });
+  h_poff[n_seqs] = (uint32_t)units;
+  return nh_classify_batch_packed(s, s->h_codes, s->h_valid, h_poff, offsets, n_seqs, out_call, out_keep, stats);
+}
 
 extern "C" int nh_debug_minimizers(nh_session *s, const uint8_t *bases, const uint64_t *offsets,
                                    uint64_t n_seqs, const uint64_t *pos_offsets, uint64_t *out_min,

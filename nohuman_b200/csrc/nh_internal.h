@@ -22,6 +22,9 @@ enum {
   NH_NUM_EVENTS
 };
 
+struct NhPackPool;
+void nh_pack_pool_destroy(NhPackPool *p); /* defined next to the pool (nh_capi.cu) */
+
 struct nh_db {
   nh_db_info_t info{};
   NhDbParams params{};
@@ -62,6 +65,12 @@ struct nh_session {
   uint8_t *d_codes = nullptr;  /* packed input planes (nh_classify_batch_packed), allocated on first use */
   uint32_t *d_valid = nullptr, *d_poff = nullptr;
   bool packed_next = false;    /* the batch being enqueued came packed */
+  /* nh_classify_batch_pack: the packer threads and the pinned planes they fill */
+  NhPackPool *pack_pool = nullptr;
+  int pack_threads = 0;
+  uint8_t *h_codes = nullptr;
+  uint32_t *h_valid = nullptr, *h_poff = nullptr;
+  cudaEvent_t ev_block = nullptr; /* blocking-sync event: the calling thread sleeps instead of spinning */
   uint64_t last_seqs = 0;
   bool use_fused = false, last_fused = false;
   int lane_taxa = NH_LANE_TAXA;
@@ -78,6 +87,11 @@ struct nh_session {
   uint32_t last_launches = 0;
   uint64_t last_units = 0, last_bases = 0;
 };
+
+/* nh_pack.cc: sequences [s0, s1) of a batch into the planes (poff already holds their first units); AVX2 with
+ * non-temporal stores when the CPU has it */
+void nh_pack_range(const uint8_t *bases, const uint64_t *offsets, uint64_t total_bases, uint64_t s0, uint64_t s1, uint8_t *codes,
+                   uint32_t *valid, const uint32_t *poff);
 
 int nh_set_error(int code, const char *fmt, ...);
 int nh_session_create_ex(nh_db *db, const nh_params_t *params, bool need_lookups, nh_session **out);

@@ -240,6 +240,15 @@ def test_packed_input_matches_ascii_and_oracle(small_db, gpu_db, mode, monkeypat
             call, keep, st = sess.classify_packed(bases, offsets, threads=3)
             icall, tk, hg = sess.debug_last_batch(len(call))
             call_a, keep_a, _ = sess.classify(bases, offsets)
+            # ASCII in, packed inside the call by the session's pool (1 and 5 packing threads)
+            for threads in (1, 5):
+                call_p, keep_p, st_p = sess.classify_pack(bases, offsets, threads=threads)
+                icall_p, tk_p, hg_p = sess.debug_last_batch(len(call_p))
+                np.testing.assert_array_equal(call_p, want["ext"])
+                np.testing.assert_array_equal(keep_p, keep_a)
+                np.testing.assert_array_equal(tk_p, want["total_kmers"])
+                np.testing.assert_array_equal(hg_p, want["hit_groups"])
+                assert st_p.fused_kernel == 2
         np.testing.assert_array_equal(tk, want["total_kmers"])
         np.testing.assert_array_equal(hg, want["hit_groups"])
         np.testing.assert_array_equal(call, want["ext"])

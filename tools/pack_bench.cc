@@ -13,6 +13,19 @@
 #include <vector>
 
 // 32 bases per iteration: codes -> 8 bytes, ambiguity -> 32 bits
+template <int MODE> /* 0 plain stores, 1 non-temporal stores, 2 plain stores wrapped into a ring of RING input bytes */
+static void pack_avx2_m(const uint8_t *in, size_t n, uint8_t *codes, uint32_t *amb, size_t ring);
+static size_t g_pf_dist = 1024;
+static int g_pf_hint = 0; /* 0 NTA, 1 T0, 2 T1, 3 T2, 4 none */
+static inline void pf(const uint8_t *p) {
+  switch (g_pf_hint) {
+    case 0: _mm_prefetch((const char *)p, _MM_HINT_NTA); break;
+    case 1: _mm_prefetch((const char *)p, _MM_HINT_T0); break;
+    case 2: _mm_prefetch((const char *)p, _MM_HINT_T1); break;
+    case 3: _mm_prefetch((const char *)p, _MM_HINT_T2); break;
+    default: break;
+  }
+}
 static void pack_avx2(const uint8_t *in, size_t n, uint8_t *codes, uint32_t *amb) {
   const __m256i m3 = _mm256_set1_epi8(3), mdf = _mm256_set1_epi8((char)0xDF);
   const __m256i lutv = _mm256_setr_epi8('A', 'C', 'T', 'G', 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 'A', 'C', 'T', 'G', 0, 0, 0, 0, 0, 0,
@@ -54,6 +67,38 @@ static void pack_avx2(const uint8_t *in, size_t n, uint8_t *codes, uint32_t *amb
   }
 }
 
+template <int MODE>
+static void pack_avx2_m(const uint8_t *in, size_t n, uint8_t *codes, uint32_t *amb, size_t ring) {
+  const __m256i m3 = _mm256_set1_epi8(3), mdf = _mm256_set1_epi8((char)0xDF);
+  const __m256i w1 = _mm256_set1_epi16(0x0104), w2 = _mm256_set1_epi32(0x00010010);
+  const __m256i gather = _mm256_setr_epi8(0, 4, 8, 12, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, 0, 4, 8, 12, -1, -1, -1, -1, -1,
+                                          -1, -1, -1, -1, -1, -1, -1);
+  const __m256i expA = _mm256_setr_epi8('A', 'C', 'G', 'T', 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 'A', 'C', 'G', 'T', 0, 0, 0, 0, 0, 0,
+                                        0, 0, 0, 0, 0, 0);
+  size_t o = 0;
+  for (size_t i = 0; i + 32 <= n; i += 32, o += 32) {
+    if (MODE == 2 && o >= ring) o = 0;
+    if ((i & 63) == 0) pf(in + i + g_pf_dist);
+    const __m256i v = _mm256_loadu_si256((const __m256i *)(in + i));
+    const __m256i s1 = _mm256_and_si256(_mm256_srli_epi16(v, 1), _mm256_set1_epi8(0x7F));
+    const __m256i s2 = _mm256_and_si256(_mm256_srli_epi16(v, 2), _mm256_set1_epi8(0x3F));
+    const __m256i code = _mm256_and_si256(_mm256_xor_si256(s1, s2), m3);
+    const __m256i expect = _mm256_shuffle_epi8(expA, code);
+    const uint32_t ok = (uint32_t)_mm256_movemask_epi8(_mm256_cmpeq_epi8(_mm256_and_si256(v, mdf), expect));
+    const __m256i p32 = _mm256_madd_epi16(_mm256_maddubs_epi16(code, w1), w2);
+    const __m256i g = _mm256_shuffle_epi8(p32, gather);
+    const uint64_t both = (uint32_t)_mm256_extract_epi32(g, 0) | (uint64_t)(uint32_t)_mm256_extract_epi32(g, 4) << 32;
+    if (MODE == 1) {
+      _mm_stream_si64((long long *)(codes + o / 4), (long long)both);
+      _mm_stream_si32((int *)(amb + o / 32), (int)~ok);
+    } else {
+      memcpy(codes + o / 4, &both, 8);
+      amb[o / 32] = ~ok;
+    }
+  }
+  if (MODE == 1) _mm_sfence();
+}
+
 int main(int argc, char **argv) {
   const size_t mb = argc > 1 ? atoi(argv[1]) : 300;
   const size_t n = mb << 20;
@@ -78,6 +123,8 @@ int main(int argc, char **argv) {
     }
   }
   std::vector<int> ts;
+  if (getenv("PF_DIST")) g_pf_dist = (size_t)atol(getenv("PF_DIST"));
+  if (getenv("PF_HINT")) g_pf_hint = atoi(getenv("PF_HINT"));
   for (int i = 2; i < argc; i++) ts.push_back(atoi(argv[i]));
   if (ts.empty()) ts = {1, 2, 4, 8, 16, 32};
   for (int t : ts) {
@@ -105,7 +152,26 @@ int main(int argc, char **argv) {
       for (auto &h : th) h.join();
       best_cp = std::min(best_cp, std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
     }
-    printf("{\"threads\": %d, \"pack_gbases_s\": %.2f, \"memcpy_gbases_s\": %.2f}\n", t, n / best / 1e9, n / best_cp / 1e9);
+    /* store policies: does the output have to travel to DRAM (and be read for ownership first)? */
+    double best_m[3] = {1e9, 1e9, 1e9};
+    const size_t ring = 1 << 21; /* 2 MiB of input = 0.75 MiB of output per thread, rewritten in place */
+    for (int mode = 0; mode < 3; mode++)
+      for (int rep = 0; rep < 4; rep++) {
+        auto t0 = std::chrono::steady_clock::now();
+        std::vector<std::thread> th;
+        for (int k = 0; k < t; k++)
+          th.emplace_back([&, k, mode] {
+            const size_t per = (n / t) & ~(size_t)127, o = per * k;
+            if (mode == 0) pack_avx2_m<0>(in.data() + o, per, codes.data() + o / 4, amb.data() + o / 32, 0);
+            if (mode == 1) pack_avx2_m<1>(in.data() + o, per, codes.data() + o / 4, amb.data() + o / 32, 0);
+            if (mode == 2) pack_avx2_m<2>(in.data() + o, per, codes.data() + (size_t)k * ring / 4, amb.data() + (size_t)k * ring / 32, ring);
+          });
+        for (auto &h : th) h.join();
+        best_m[mode] = std::min(best_m[mode], std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+      }
+    printf("{\"pf_hint\": %d, \"pf_dist\": %zu, \"threads\": %d, \"input_mb\": %zu, \"pack_gbases_s\": %.2f, \"memcpy_gbases_s\": %.2f, \"prefetch_plain_gbases_s\": %.2f, "
+           "\"prefetch_nt_store_gbases_s\": %.2f, \"prefetch_ring_gbases_s\": %.2f}\n",
+           g_pf_hint, g_pf_dist, t, mb, n / best / 1e9, n / best_cp / 1e9, n / best_m[0] / 1e9, n / best_m[1] / 1e9, n / best_m[2] / 1e9);
   }
   return 0;
 }
