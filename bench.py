@@ -66,7 +66,7 @@ def parse_args():
     ap.add_argument("--workload-mbases", type=int, default=150, help="bases per GPU of each `workloads` entry")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--e2e-packed", default="6x6,8x4,4x8", help="packed e2e shapes 'workers x pack threads' (0 = cores / workers), "
+    ap.add_argument("--e2e-packed", default="8x4,6x6,6x4", help="packed e2e shapes 'workers x pack threads' (0 = cores / workers), "
                     "comma separated; the best one is reported, all are listed")
     ap.add_argument("--no-workloads", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
@@ -620,7 +620,7 @@ def run_e2e(args, torch, dist, db, bufs, d_off, n_pairs, n_seqs, total, world, s
 
     Two transfer formats for the same ASCII host buffers: "ascii" = nh_classify_batch (1 byte per base over
     PCIe, no host core involved); "packed" = nh_classify_batch_pack (the host cores pack INSIDE the timed region,
-    0.48 byte per base crosses PCIe), run with several sessions on as many host threads so that the cores keep
+    0.43 byte per base crosses PCIe), run with several sessions on as many host threads so that the cores keep
     packing while other sessions' copies and kernels run.  Packing needs the host's cores and memory bandwidth,
     so it is measured at N = 1 only (one process per host); `e2e` is the better of the two."""
     from nohuman_b200 import Session
@@ -683,7 +683,7 @@ def run_e2e(args, torch, dist, db, bufs, d_off, n_pairs, n_seqs, total, world, s
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
         calls = outs[0][0].clone()
-        h2d = (total + (n_seqs + 1) * 8) if fmt == "ascii" else (units * 12 + (n_seqs + 1) * 12)
+        h2d = (total + (n_seqs + 1) * 8) if fmt == "ascii" else (units * 12 + n_seqs * 4)
         return {"value": round(world * steps * n_launch * n_pairs * 2 * READ_LEN / dt / 1e9, 3), "unit": UNIT,
                 "h2d_bytes_per_step": int(n_launch * h2d), "d2h_bytes_per_step": int(n_launch * n_pairs * 5),
                 "ms_per_step": round(dt / steps * 1e3, 4), "steps": steps}, calls
@@ -705,7 +705,7 @@ def run_e2e(args, torch, dist, db, bufs, d_off, n_pairs, n_seqs, total, world, s
             if res_p is None or (r["same_calls_as_ascii"] and r["value"] > res_p["value"]):
                 res_p = r
         res_p["input_format"] = ("ASCII host buffers handed to nh_classify_batch_pack: packed by the host cores INSIDE the timed region "
-                                 "(AVX2, 2-bit codes + validity bits), 0.48 byte per base over PCIe")
+                                 "(AVX2, 2-bit codes + validity bits), 0.43 byte per base over PCIe")
         if len(sweep) > 1:
             res_p["shapes_tried"] = sweep
         formats["packed"] = res_p

@@ -15,6 +15,7 @@
 #include <sys/stat.h>
 
 #include <algorithm>
+#include <atomic>
 #include <condition_variable>
 #include <functional>
 #include <mutex>
@@ -755,6 +756,9 @@ extern "C" void nh_session_destroy(nh_session *s) {
   if (s->h_codes) cudaFreeHost(s->h_codes);
   if (s->h_valid) cudaFreeHost(s->h_valid);
   if (s->h_poff) cudaFreeHost(s->h_poff);
+  if (s->h_len32) cudaFreeHost(s->h_len32);
+  cudaFree(s->d_len32);
+  cudaFree(s->d_len_sums);
   if (s->ev_block) cudaEventDestroy(s->ev_block);
   if (s->h_counters) cudaFreeHost(s->h_counters);
   for (int i = 0; i < NH_NUM_EVENTS; i++)
@@ -982,9 +986,11 @@ static int ensure_packed_planes(nh_session *s, uint64_t cap_units) {
 /* Packed host input: 2-bit codes + validity bits + unit offsets (nh_pack_reads) instead of ASCII.
  * 0.4 bytes per base cross PCIe; the kernel instantiation that reads the planes also skips the
  * ASCII -> 2-bit step. */
-extern "C" int nh_classify_batch_packed(nh_session *s, const uint8_t *codes, const uint32_t *valid, const uint32_t *poff,
-                                        const uint64_t *offsets, uint64_t n_seqs, uint32_t *out_call, uint8_t *out_keep,
-                                        nh_batch_stats_t *stats) {
+/* len32 != nullptr: the per-sequence metadata travels as 4-byte lengths and the device rebuilds offsets and
+ * first units (nh_classify_batch_pack); otherwise poff and offsets are copied as they are */
+static int classify_packed_impl(nh_session *s, const uint8_t *codes, const uint32_t *valid, const uint32_t *poff,
+                                const uint64_t *offsets, const uint32_t *len32, uint64_t n_seqs, uint32_t *out_call,
+                                uint8_t *out_keep, nh_batch_stats_t *stats) {
   if (!s || !offsets || !poff || (n_seqs && offsets[n_seqs] > 0 && (!codes || !valid)))
     return nh_set_error(NH_ERR_INVALID, "null argument");
   if (!s->use_fused) return nh_set_error(NH_ERR_UNSUPPORTED, "packed input needs the streaming kernel (window of 5 l-mers)");
@@ -1011,12 +1017,25 @@ extern "C" int nh_classify_batch_packed(nh_session *s, const uint8_t *codes, con
     CUDA_TRY(cudaMemcpyAsync(s->d_codes, codes, units * 8, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(s->d_valid, valid, units * 4, cudaMemcpyHostToDevice, st));
   }
-  CUDA_TRY(cudaMemcpyAsync(s->d_poff, poff, (n_seqs + 1) * 4, cudaMemcpyHostToDevice, st));
-  CUDA_TRY(cudaMemcpyAsync(s->d_offsets, offsets, (n_seqs + 1) * 8, cudaMemcpyHostToDevice, st));
+  uint32_t extra_launches = 0;
+  if (len32) {
+    if (!s->d_len32) {
+      cudaError_t e = cudaMalloc(&s->d_len32, (s->cap_seqs + 1) * 4);
+      if (e == cudaSuccess) e = cudaMalloc(&s->d_len_sums, (s->cap_seqs / 1024 + 2) * 16);
+      if (e != cudaSuccess) return nh_set_error(NH_ERR_NOMEM, "allocating the length scan failed: %s", cudaGetErrorString(e));
+      s->device_bytes += (s->cap_seqs + 1) * 4 + (s->cap_seqs / 1024 + 2) * 16;
+    }
+    CUDA_TRY(cudaMemcpyAsync(s->d_len32, len32, n_seqs * 4, cudaMemcpyHostToDevice, st));
+    extra_launches = (uint32_t)nh_launch_len_scan(s->d_len32, (uint32_t)n_seqs, s->d_len_sums, s->d_offsets, s->d_poff, st);
+  } else {
+    CUDA_TRY(cudaMemcpyAsync(s->d_poff, poff, (n_seqs + 1) * 4, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(s->d_offsets, offsets, (n_seqs + 1) * 8, cudaMemcpyHostToDevice, st));
+  }
   s->packed_next = true;
   rc = enqueue_batch(s, nullptr, s->d_offsets, n_seqs, total, s->d_out_call, s->d_out_keep, true, nullptr, nullptr, nullptr);
   s->packed_next = false;
   if (rc) return rc;
+  s->last_launches += extra_launches;
   if (out_call) CUDA_TRY(cudaMemcpyAsync(out_call, s->d_out_call, n_units * 4, cudaMemcpyDeviceToHost, st));
   if (out_keep) CUDA_TRY(cudaMemcpyAsync(out_keep, s->d_out_keep, n_units, cudaMemcpyDeviceToHost, st));
   cudaEventRecord(s->ev[EV_D2H1], st);
@@ -1027,6 +1046,12 @@ extern "C" int nh_classify_batch_packed(nh_session *s, const uint8_t *codes, con
   CUDA_TRY(cudaEventRecord(s->ev_block, st));
   CUDA_TRY(cudaEventSynchronize(s->ev_block));
   return nh_session_sync(s, stats);
+}
+
+extern "C" int nh_classify_batch_packed(nh_session *s, const uint8_t *codes, const uint32_t *valid, const uint32_t *poff,
+                                        const uint64_t *offsets, uint64_t n_seqs, uint32_t *out_call, uint8_t *out_keep,
+                                        nh_batch_stats_t *stats) {
+  return classify_packed_impl(s, codes, valid, poff, offsets, nullptr, n_seqs, out_call, out_keep, stats);
 }
 
 /* ------------------------------------------------------------------ */
@@ -1116,6 +1141,7 @@ extern "C" int nh_classify_batch_pack(nh_session *s, const uint8_t *bases, const
     cudaError_t e = cudaMallocHost(&s->h_codes, cap_units * 8 + 64);
     if (e == cudaSuccess) e = cudaMallocHost(&s->h_valid, cap_units * 4 + 64);
     if (e == cudaSuccess) e = cudaMallocHost(&s->h_poff, (s->cap_seqs + 1) * 4);
+    if (e == cudaSuccess) e = cudaMallocHost(&s->h_len32, (s->cap_seqs + 1) * 4);
     if (e != cudaSuccess) return nh_set_error(NH_ERR_NOMEM, "pinned planes for the packed batch: %s", cudaGetErrorString(e));
   }
   /* units per thread range; prefix over the ranges; unit offsets and the planes of every range */
@@ -1134,19 +1160,26 @@ extern "C" int nh_classify_batch_pack(nh_session *s, const uint8_t *bases, const
   const uint64_t units = part[(size_t)T];
   if (units > cap_units || units > 0xFFFFFFFFull)
     return nh_set_error(NH_ERR_CAPACITY, "packed batch has %llu units, session holds %llu", (unsigned long long)units, (unsigned long long)cap_units);
-  uint32_t *h_poff = s->h_poff;
+  uint32_t *h_poff = s->h_poff, *h_len32 = s->h_len32;
+  std::atomic<int> too_long{0};
   s->pack_pool->run([&](int t) {
     uint64_t a, b;
     range(t, &a, &b);
     uint64_t u = part[(size_t)t];
     for (uint64_t q = a; q < b; q++) {
+      const uint64_t len = offsets[q + 1] - offsets[q];
+      if (len > 0xFFFFFFFFull) too_long.store(1);
       h_poff[q] = (uint32_t)u;
-      u += (offsets[q + 1] - offsets[q] + 31) >> 5;
+      h_len32[q] = (uint32_t)len;
+      u += (len + 31) >> 5;
     }
     nh_pack_range(bases, offsets, total, a, b, s->h_codes, s->h_valid, h_poff);
   });
   h_poff[n_seqs] = (uint32_t)units;
-  return nh_classify_batch_packed(s, s->h_codes, s->h_valid, h_poff, offsets, n_seqs, out_call, out_keep, stats);
+  /* 4 bytes per sequence cross PCIe (lengths); the device rebuilds offsets and first units */
+  static const bool send_offsets = getenv("NH_PACK_SEND_OFFSETS") != nullptr; /* A/B switch: 12 bytes per sequence as before */
+  return classify_packed_impl(s, s->h_codes, s->h_valid, h_poff, offsets, too_long.load() || send_offsets ? nullptr : h_len32, n_seqs,
+                              out_call, out_keep, stats);
 }
 
 extern "C" int nh_debug_minimizers(nh_session *s, const uint8_t *bases, const uint64_t *offsets,

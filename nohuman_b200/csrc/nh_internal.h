@@ -69,7 +69,9 @@ struct nh_session {
   NhPackPool *pack_pool = nullptr;
   int pack_threads = 0;
   uint8_t *h_codes = nullptr;
-  uint32_t *h_valid = nullptr, *h_poff = nullptr;
+  uint32_t *h_valid = nullptr, *h_poff = nullptr, *h_len32 = nullptr;
+  uint32_t *d_len32 = nullptr; /* sequence lengths as sent; k_len_* rebuild d_offsets and d_poff from them */
+  uint64_t *d_len_sums = nullptr;
   cudaEvent_t ev_block = nullptr; /* blocking-sync event: the calling thread sleeps instead of spinning */
   uint64_t last_seqs = 0;
   bool use_fused = false, last_fused = false;

@@ -182,6 +182,64 @@ k_plan_fill(const uint64_t *__restrict__ off, uint32_t n_seqs, int k, int tile_p
   if (s == 0) tile_base[n_seqs] = counters->n_tiles;
 }
 
+/* Sequence lengths -> what the kernels read: base offsets (u64) and, for packed input, every sequence's
+ * first unit of 32 bases (u32).  nh_classify_batch_pack sends 4 bytes per sequence instead of 12. */
+__global__ void __launch_bounds__(PLAN_THREADS)
+k_len_count(const uint32_t *__restrict__ len, uint32_t n_seqs, uint64_t *__restrict__ sums /* [2 * blocks] */) {
+  __shared__ uint64_t s_warp[33];
+  const uint32_t s = blockIdx.x * PLAN_THREADS + threadIdx.x;
+  const uint64_t l = s < n_seqs ? len[s] : 0;
+  uint64_t total_l, total_u;
+  block_excl_scan(l, &total_l, s_warp);
+  block_excl_scan((l + 31) >> 5, &total_u, s_warp);
+  if (threadIdx.x == 0) {
+    sums[2u * blockIdx.x] = total_l;
+    sums[2u * blockIdx.x + 1u] = total_u;
+  }
+}
+
+__global__ void __launch_bounds__(PLAN_THREADS)
+k_len_scan(uint64_t *__restrict__ sums, uint32_t nb) {
+  __shared__ uint64_t s_warp[33];
+  __shared__ uint64_t s_run[2];
+  if (threadIdx.x < 2) s_run[threadIdx.x] = 0;
+  __syncthreads();
+  for (uint32_t base = 0; base < nb; base += PLAN_THREADS) {
+    const uint32_t i = base + threadIdx.x;
+#pragma unroll
+    for (uint32_t q = 0; q < 2; q++) {
+      const uint64_t v = i < nb ? sums[2u * i + q] : 0;
+      uint64_t total;
+      const uint64_t ex = block_excl_scan(v, &total, s_warp);
+      const uint64_t run = s_run[q];
+      if (i < nb) sums[2u * i + q] = run + ex;
+      __syncthreads();
+      if (threadIdx.x == 0) s_run[q] = run + total;
+      __syncthreads();
+    }
+  }
+}
+
+__global__ void __launch_bounds__(PLAN_THREADS)
+k_len_fill(const uint32_t *__restrict__ len, uint32_t n_seqs, const uint64_t *__restrict__ sums,
+           uint64_t *__restrict__ off /* [n_seqs + 1] */, uint32_t *__restrict__ poff /* [n_seqs + 1] */) {
+  __shared__ uint64_t s_warp[33];
+  const uint32_t s = blockIdx.x * PLAN_THREADS + threadIdx.x;
+  const uint64_t l = s < n_seqs ? len[s] : 0;
+  uint64_t total;
+  const uint64_t ex_l = block_excl_scan(l, &total, s_warp);
+  const uint64_t ex_u = block_excl_scan((l + 31) >> 5, &total, s_warp);
+  if (s < n_seqs) {
+    const uint64_t o = sums[2u * blockIdx.x] + ex_l, u = sums[2u * blockIdx.x + 1u] + ex_u;
+    off[s] = o;
+    poff[s] = (uint32_t)u;
+    if (s == n_seqs - 1u) {
+      off[n_seqs] = o + l;
+      poff[n_seqs] = (uint32_t)(u + ((l + 31) >> 5));
+    }
+  }
+}
+
 /* The tile descriptors of a batch of long reads, one thread per tile (a 100 kb read has 400 tiles:
  * one thread writing them all was 7 % of a step of 50 kb reads).  The sequence of a tile is found
  * by bisection over tile_base. */
@@ -1611,6 +1669,15 @@ cudaError_t nh_kernels_init(void) {
   NH_SET_SMEM((k_stream_classify<5, 0, false, true, false, true>), smax)
 #undef NH_SET_SMEM
   return cudaSuccess;
+}
+
+int nh_launch_len_scan(const uint32_t *len, uint32_t n_seqs, uint64_t *sums, uint64_t *off, uint32_t *poff, cudaStream_t st) {
+  const uint32_t nb = (n_seqs + PLAN_THREADS - 1) / PLAN_THREADS;
+  if (nb == 0) return 0;
+  k_len_count<<<nb, PLAN_THREADS, 0, st>>>(len, n_seqs, sums);
+  k_len_scan<<<1, PLAN_THREADS, 0, st>>>(sums, nb);
+  k_len_fill<<<nb, PLAN_THREADS, 0, st>>>(len, n_seqs, sums, off, poff);
+  return 3;
 }
 
 int nh_launch_plan(const NhDbParams &db, const NhBatchPtrs &b, cudaStream_t st) {

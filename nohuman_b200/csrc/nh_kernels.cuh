@@ -150,6 +150,8 @@ struct NhScoreParams {
 
 /* launchers (nh_kernels.cu); each returns the number of kernels launched */
 int nh_launch_plan(const NhDbParams &db, const NhBatchPtrs &b, cudaStream_t st);
+/* sequence lengths -> base offsets and first units (sums: 2 * ceil(n_seqs / 1024) words of scratch); returns the launches */
+int nh_launch_len_scan(const uint32_t *len, uint32_t n_seqs, uint64_t *sums, uint64_t *off, uint32_t *poff, cudaStream_t st);
 /* streaming path: lane-serial minimizer scan feeding the probe, in-warp scoring */
 bool nh_fused_supported(const NhDbParams &db);
 int nh_launch_stream(const NhDbParams &db, const NhBatchPtrs &b, const NhScoreParams &sp,
