@@ -255,3 +255,36 @@ def test_packed_input_matches_ascii_and_oracle(small_db, gpu_db, mode, monkeypat
         np.testing.assert_array_equal(call, call_a)
         np.testing.assert_array_equal(keep, keep_a)
         assert st.fused_kernel == 2
+
+
+def test_pack_entry_with_a_million_short_sequences(small_db, gpu_db):
+    """nh_classify_batch_pack sends 4-byte lengths and rebuilds offsets / first units on the device (k_len_*):
+    1.3 M sequences (more than one pass of the single-block scan), lengths 0..90 with many empties, against the
+    ASCII entry point for all of them and against the oracle for a prefix."""
+    from nohuman_b200 import Session
+    rng = np.random.default_rng(77)
+    g = np.asarray(dict(small_db.genomes)[9606])
+    n = 1_300_001
+    lens = rng.integers(30, 91, n)
+    lens[rng.random(n) < 0.05] = 0
+    lens[rng.random(n) < 0.02] = 1
+    lens[-1] = 0
+    offsets = np.zeros(n + 1, np.uint64)
+    np.cumsum(lens, out=offsets[1:])
+    total = int(offsets[-1])
+    # read i is the slice of the human genome starting at 37 i (wrapping), so most k-mers hit the table
+    starts = (np.arange(n, dtype=np.int64) * 37) % (len(g) - 200)
+    within = np.arange(total, dtype=np.int64) - np.repeat(offsets[:-1].astype(np.int64), lens)
+    bases = g[np.repeat(starts, lens) + within].astype(np.uint8)
+    bases[rng.random(total) < 0.002] = ord("N")
+    small_db.confidence = 0.0
+    with Session(gpu_db, confidence=0.0, paired=False, max_batch_bases=total + 4096, max_batch_seqs=n) as sess:
+        call_a, keep_a, _ = sess.classify(bases, offsets)
+        call_p, keep_p, st = sess.classify_pack(bases, offsets, threads=7)
+        assert st.fused_kernel == 2
+    np.testing.assert_array_equal(call_p, call_a)
+    np.testing.assert_array_equal(keep_p, keep_a)
+    m = 20_000
+    want = small_db.classify_batch(bases[:int(offsets[m])], offsets[:m + 1], paired=False)
+    np.testing.assert_array_equal(call_p[:m], want["ext"])
+    assert (call_p != 0).sum() > n // 10
