@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define NH_ABI_VERSION 2
+#define NH_ABI_VERSION 3
 
 typedef enum {
   NH_OK = 0,
@@ -64,6 +64,8 @@ typedef struct {
   uint64_t node_count;
   int32_t device;
   int32_t replicated_by; /* 0: read from disk / memory, 1: NCCL broadcast, 2: peer-copy tree (nh_db_open_multi) */
+  uint64_t filter_bytes; /* size of the miss filter built next to the table on the device (capacity / 32 records of 32
+                          * bytes; 0: none — NH_FILTER=0, or no memory for it) */
 } nh_db_info_t;
 
 typedef struct {

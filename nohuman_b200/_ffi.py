@@ -39,6 +39,7 @@ class DbInfo(C.Structure):
         ("capacity", C.c_uint64), ("size", C.c_uint64), ("key_bits", C.c_uint64),
         ("value_bits", C.c_uint64), ("node_count", C.c_uint64),
         ("device", C.c_int32), ("replicated_by", C.c_int32),
+        ("filter_bytes", C.c_uint64),
     ]
 
 

@@ -161,7 +161,7 @@ static int parse_opts_taxo(nh_db *db, const void *opts, size_t opts_len, const v
   return NH_OK;
 }
 
-static int finish_db(nh_db *db, const uint64_t hdr[4]) {
+static int finish_db(nh_db *db, const uint64_t hdr[4], bool cells_ready = true) {
   nh_db_info_t &I = db->info;
   I.capacity = hdr[0];
   I.size = hdr[1];
@@ -222,6 +222,32 @@ static int finish_db(nh_db *db, const uint64_t hdr[4]) {
   CUDA_TRY(cudaGetDeviceProperties(&prop, db->info.device));
   db->sm_count = prop.multiProcessorCount;
   CUDA_TRY(nh_kernels_init());
+  return cells_ready ? nh_db_build_filter(db) : NH_OK;
+}
+
+/* The miss filter of the table on db's device (nh_kernels.cu, k_filter_build): capacity / 32 records of 32 bytes,
+ * a quarter of the table's size.  Built when the cells are on the device; NH_FILTER=0 turns it off, and a failed
+ * allocation only means the kernels run without it. */
+int nh_db_build_filter(nh_db *db) {
+  const char *e = getenv("NH_FILTER");
+  if (e && e[0] == '0') return NH_OK;
+  NhDbParams &P = db->params;
+  const uint64_t n_blocks = (P.capacity + 31) / 32;
+  /* value_bits >= 5: the kernel keeps a chain's cell offset (0..31) in the bits of a compacted key that the value would occupy */
+  if (!nh_fused_supported(P) || n_blocks > 0xFFFFFFFFull || P.cells == nullptr || P.value_bits < 5) return NH_OK;
+  CUDA_TRY(cudaSetDevice(db->info.device));
+  if (!db->d_filter) {
+    if (cudaMalloc(&db->d_filter, n_blocks * 32) != cudaSuccess) {
+      cudaGetLastError();
+      db->d_filter = nullptr;
+      return NH_OK;
+    }
+  }
+  nh_launch_filter_build(P, db->d_filter, (uint32_t)n_blocks, nullptr);
+  const cudaError_t ce = cudaDeviceSynchronize();
+  if (ce != cudaSuccess) return nh_set_error(NH_ERR_CUDA, "building the miss filter failed: %s", cudaGetErrorString(ce));
+  db->n_filter_blocks = (uint32_t)n_blocks; /* handed to the kernels in NhScoreParams */
+  db->info.filter_bytes = n_blocks * 32;
   return NH_OK;
 }
 
@@ -311,7 +337,7 @@ int nh_db_create_empty(const void *opts, size_t opts_len, const void *taxo, size
   db->owns_cells = true;
   cudaMemset(db->d_cells, 0, bytes);
   const uint64_t hdr[4] = {capacity, 0, 32 - vb, vb};
-  rc = finish_db(db, hdr);
+  rc = finish_db(db, hdr, false); /* the builder fills the cells and calls nh_db_build_filter when it is done */
   if (rc) {
     nh_db_close(db);
     return rc;
@@ -606,6 +632,7 @@ extern "C" void nh_db_close(nh_db *db) {
   if (db->d_parent) cudaFree(db->d_parent);
   if (db->d_ext) cudaFree(db->d_ext);
   if (db->d_huge) cudaFree(db->d_huge);
+  if (db->d_filter) cudaFree(db->d_filter);
   delete db;
 }
 
@@ -648,6 +675,11 @@ int nh_session_create_ex(nh_db *db, const nh_params_t *params, bool need_lookups
     const char *lt = getenv("NH_TEST_LANE_TAXA");
     int v = lt ? atoi(lt) : NH_LANE_TAXA;
     s->lane_taxa = v < 1 ? 1 : (v > NH_LANE_TAXA ? NH_LANE_TAXA : v);
+    /* NH_FILTER_MODE: 0 the streaming kernel never asks the miss filter, 1 (default) units without a hit so far ask
+     * it before the table, 2 every lookup does */
+    const char *fm = getenv("NH_FILTER_MODE");
+    s->filter_mode = fm ? atoi(fm) : 1;
+    if (s->filter_mode < 0 || s->filter_mode > 2) s->filter_mode = 1;
     /* NH_FUSED_TILE_POS=n fixes the tile size of the streaming kernel (default: by mean read length) */
     const char *tp = getenv("NH_FUSED_TILE_POS");
     s->forced_tile_pos = tp ? atoi(tp) : 0;
@@ -833,6 +865,9 @@ static int enqueue_batch(nh_session *s, const uint8_t *d_bases, const uint64_t *
   SP.min_hit_groups = s->params.minimum_hit_groups;
   SP.keep_human = s->params.keep_human;
   SP.lane_taxa = s->lane_taxa;
+  SP.filter_mode = s->filter_mode;
+  SP.filter = s->db->n_filter_blocks ? s->db->d_filter : nullptr;
+  SP.n_filter_blocks = s->db->n_filter_blocks;
   const int sm = s->db->sm_count;
   uint64_t tiles_upper = n_seqs + total_bases / (uint64_t)P.tile_pos + 1;
   uint64_t lookups_upper = total_bases;

@@ -32,6 +32,8 @@ struct nh_db {
   bool owns_cells = false;
   uint32_t *d_parent = nullptr;
   uint32_t *d_ext = nullptr;
+  uint32_t *d_filter = nullptr; /* miss filter: one 32-byte record per block of 32 cells (k_filter_build) */
+  uint32_t n_filter_blocks = 0; /* 0 until the filter is built */
   uint32_t *d_huge = nullptr; /* global-memory taxon table for units with more distinct taxa than shared memory holds */
   std::vector<uint32_t> h_parent, h_ext;
   std::vector<uint64_t> h_ext64;
@@ -76,6 +78,7 @@ struct nh_session {
   uint64_t last_seqs = 0;
   bool use_fused = false, last_fused = false;
   int lane_taxa = NH_LANE_TAXA;
+  int filter_mode = 1;
   int last_form = 0;       /* 0: warp-per-tile kernels, 2: k_stream_classify */
   int forced_tile_pos = 0; /* NH_FUSED_TILE_POS */
   NhTileTab *d_tile_tab = nullptr;
@@ -96,6 +99,7 @@ void nh_pack_range(const uint8_t *bases, const uint64_t *offsets, uint64_t total
                    uint32_t *valid, const uint32_t *poff);
 
 int nh_set_error(int code, const char *fmt, ...);
+int nh_db_build_filter(nh_db *db); /* after the cells are on the device (every open path; the synthetic builder calls it itself) */
 int nh_session_create_ex(nh_db *db, const nh_params_t *params, bool need_lookups, nh_session **out);
 int nh_resolve_db_dir(const char *db_dir, std::string &out);
 

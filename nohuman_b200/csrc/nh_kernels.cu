@@ -870,6 +870,7 @@ k_score_big(const NhDbParams db, const NhBatchPtrs b, const NhScoreParams sp) {
 #endif
 #define NH_META_FIRST 0x8000u /* the first lookup of its tile */
 #define NH_AUX_NONE 0xFFFFFFFFu
+#define NH_AUX_FILTER 0x80000000u /* FILTER kernels: the request in flight is a filter record, not a table sector */
 
 template <bool EMIT>
 struct __align__(16) StreamWarpSmem {
@@ -956,6 +957,65 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
   return v;
 }
 
+
+/* ------------------------------------------------------------------ */
+/* The miss filter: one 32-byte record per block of 32 table cells, built when the database is opened.
+ * word 0: occupancy of the block's cells (cells past the table's end count as occupied);
+ * words 1-7: a partitioned Bloom filter of the compacted keys stored IN the block — one bit in words 1-2,
+ * one in 3-4, one in 5-6, one in word 7 (22 keys per block at load 0.7: about 1.3 % false positives).
+ * A probe chain that starts at cell `off` of the block and whose key is in none of the block's cells ends at
+ * the block's first free cell at or after `off`: if there is one, the lookup is a MISS after one 32-byte
+ * request instead of the 1.65 sectors a missing key walks in the table; if there is none the chain runs
+ * into the next block, whose record is asked next.  A positive answer sends the lookup to the table at the
+ * cell it had reached.  The filter never changes a result; who asks it is decided per unit (NhScoreParams). */
+__device__ __forceinline__ uint32_t nh_filter_hash(uint32_t ckey) {
+  uint32_t h = ckey * 0x9E3779B1u;
+  h ^= h >> 15;
+  h *= 0x85EBCA77u;
+  h ^= h >> 13;
+  return h;
+}
+
+__global__ void __launch_bounds__(256)
+k_filter_build(const uint32_t *__restrict__ cells, uint64_t capacity, uint32_t value_bits, uint32_t value_mask,
+               uint32_t *__restrict__ filter, uint32_t n_blocks) {
+  const uint32_t blk = blockIdx.x * blockDim.x + threadIdx.x;
+  if (blk >= n_blocks) return;
+  uint32_t rec[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) rec[i] = 0;
+  const uint64_t base = (uint64_t)blk * 32ULL;
+#pragma unroll 1
+  for (uint32_t q = 0; q < 8; q++) {
+    uint32_t c[4] = {0u, 0u, 0u, 0u};
+    if (base + q * 4u + 4u <= capacity) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4 *>(cells + base) + q);
+      c[0] = v.x; c[1] = v.y; c[2] = v.z; c[3] = v.w;
+    } else { /* the table's last cells: an adopted array need not be padded */
+      for (uint32_t j = 0; j < 4; j++)
+        if (base + q * 4u + j < capacity) c[j] = __ldg(cells + base + q * 4u + j);
+    }
+#pragma unroll
+    for (uint32_t j = 0; j < 4; j++) {
+      const uint32_t cell = q * 4u + j;
+      if (base + cell >= capacity) {
+        rec[0] |= 1u << cell;
+      } else if (c[j] & value_mask) {
+        rec[0] |= 1u << cell;
+        const uint32_t h = nh_filter_hash(c[j] >> value_bits);
+        const uint32_t i0 = h & 63u, i1 = (h >> 6) & 63u, i2 = (h >> 12) & 63u, i3 = (h >> 18) & 31u;
+        rec[1 + (i0 >> 5)] |= 1u << (i0 & 31u);
+        rec[3 + (i1 >> 5)] |= 1u << (i1 & 31u);
+        rec[5 + (i2 >> 5)] |= 1u << (i2 & 31u);
+        rec[7] |= 1u << i3;
+      }
+    }
+  }
+  uint4 *out = reinterpret_cast<uint4 *>(filter + (uint64_t)blk * 8ULL);
+  out[0] = make_uint4(rec[0], rec[1], rec[2], rec[3]);
+  out[1] = make_uint4(rec[4], rec[5], rec[6], rec[7]);
+}
+
 #ifndef NH_STREAM_CHECK_MASK
 #define NH_STREAM_CHECK_MASK 1 /* probe check after bases with (j & mask) == mask: 1 -> every 2nd base */
 #endif
@@ -964,7 +1024,7 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
  * immediates); KL = 0: any k, l with k - l + 1 = W, read from the database.
  * PACKED: the batch came as 2-bit codes + validity bits (nh_classify_batch_packed), every sequence
  * starting on a unit of 32 bases; tiles then start on units too (tile_pos is a multiple of 32). */
-template <int W, int KL, bool DBG, bool REV0, bool EMIT, bool PACKED>
+template <int W, int KL, bool DBG, bool REV0, bool EMIT, bool PACKED, bool FILTER>
 __global__ void __launch_bounds__(NH_BLOCK_THREADS, NH_STREAM_MIN_BLOCKS)
 k_stream_classify(const NhDbParams db, const NhBatchPtrs b, const NhScoreParams sp) {
   static_assert(W == 5, "the scan consumes one 4-byte word per ring rotation");
@@ -994,7 +1054,11 @@ k_stream_classify(const NhDbParams db, const NhBatchPtrs b, const NhScoreParams 
   /* cells of the last sector that exist (the allocation is zero-padded past the table's end) */
   const uint32_t last_range = (db.capacity & 7ULL) ? (1u << (uint32_t)(db.capacity & 7ULL)) - 1u : 0xFFu;
   /* probe-chain guard for a table without any empty cell (never a real database) */
-  const uint32_t max_visits = n_sectors + 1u < 0xFFFFu ? n_sectors + 1u : 0xFFFFu;
+  /* FILTER kernels keep bit 31 of the lookup state for NH_AUX_FILTER, and the cell a continuation starts at in
+   * the top value_bits (>= 5, nh_db_build_filter) bits of its compacted key */
+  const uint32_t max_visits = FILTER ? (n_sectors + 1u < 0x7FFEu ? n_sectors + 1u : 0x7FFEu) : (n_sectors + 1u < 0xFFFFu ? n_sectors + 1u : 0xFFFFu);
+  const uint32_t last_block = FILTER ? sp.n_filter_blocks - 1u : 0u;
+  const uint32_t ck_bits = 32u - db.value_bits;
   uint32_t tot_lookups = 0, tot_sectors = 0, tot_classified = 0, tot_kept = 0;
 
   const uint32_t bar0 = smem_addr(&sm.bbar[0]);
@@ -1065,6 +1129,50 @@ k_stream_classify(const NhDbParams db, const NhBatchPtrs b, const NhScoreParams 
             c[0] = lo.x; c[1] = lo.y; c[2] = lo.z; c[3] = lo.w;
             c[4] = hi.x; c[5] = hi.y; c[6] = hi.z; c[7] = hi.w;
           }
+          if (FILTER) {
+            const uint32_t ck = f_ckey & ((1u << ck_bits) - 1u);
+            const uint32_t st = f_ckey >> ck_bits; /* cell of the block / sector the chain enters at */
+            const uint32_t visits = ((f_aux >> 16) & 0x7FFFu) + 1u;
+            f_ckey = ck;
+            if (f_aux & NH_AUX_FILTER) {
+              /* the record of block f_unit */
+              const uint32_t h = nh_filter_hash(ck);
+              const uint32_t w0 = (h & 32u) ? c[2] : c[1], w1 = (h & (32u << 6)) ? c[4] : c[3], w2 = (h & (32u << 12)) ? c[6] : c[5];
+              const bool maybe = (((w0 >> (h & 31u)) & (w1 >> ((h >> 6) & 31u)) & (w2 >> ((h >> 12) & 31u)) & (c[7] >> ((h >> 18) & 31u))) & 1u) != 0u;
+              const uint32_t free_cells = ~c[0] & (0xFFFFFFFFu << st);
+              if (!maybe && free_cells != 0u) {
+                done = true; /* the key is not in the block and the chain ends in it: a miss */
+              } else if (visits >= max_visits) {
+                done = true;
+              } else if (maybe) { /* to the table, at the cell the chain has reached */
+                f_aux = (f_aux & 0xFFFFu) | (visits << 16);
+                f_unit = f_unit * 4u + (st >> 3);
+                f_ckey = ck | ((st & 7u) << ck_bits);
+              } else { /* every cell from st on is taken by other keys: the next block */
+                f_aux = (f_aux & (NH_AUX_FILTER | 0xFFFFu)) | (visits << 16);
+                f_unit = f_unit == last_block ? 0u : f_unit + 1u;
+              }
+            } else {
+              uint32_t range = 0xFFu << st;
+              if (f_unit == last_sector) range &= last_range;
+              int state = -1;
+#pragma unroll
+              for (int j = 7; j >= 0; j--) {
+                const uint32_t val = c[j] & db.value_mask;
+                const bool term = (val == 0u) || ((c[j] >> db.value_bits) == ck);
+                if (term && ((range >> j) & 1u)) state = (int)val;
+              }
+              if (state >= 0) {
+                done = true;
+                result = (uint32_t)state;
+              } else if (visits >= max_visits) {
+                done = true; /* went round a table without an empty cell */
+              } else {
+                f_aux = (f_aux & 0xFFFFu) | (visits << 16);
+                f_unit = f_unit == last_sector ? 0u : f_unit + 1u;
+              }
+            }
+          } else {
           uint32_t range = 0xFFu << f_start;
           if (f_unit == last_sector) range &= last_range;
           int state = -1;
@@ -1085,6 +1193,7 @@ k_stream_classify(const NhDbParams db, const NhBatchPtrs b, const NhScoreParams 
               f_aux = (f_aux & 0xFFFFu) | (visits << 16);
               f_unit = f_unit == last_sector ? 0u : f_unit + 1u;
             }
+          }
           }
         }
         const bool cont = active && !done;
@@ -1139,10 +1248,21 @@ k_stream_classify(const NhDbParams db, const NhBatchPtrs b, const NhScoreParams 
           if (EMIT) b.lk_taxon[f_slot] = 0u;
         } else {
           const uint64_t idx = nh_fastmod(h, db.capacity, db.mod_m, db.mod_sh1, db.mod_sh2);
-          f_unit = (uint32_t)(idx >> 3);
-          f_start = (uint32_t)idx & 7u;
-          f_ckey = (uint32_t)(h >> (32u + db.value_bits));
-          f_aux = meta; /* zero sectors visited */
+          if (FILTER) {
+            /* who asks the filter first: units none of whose lookups has hit so far (sp.filter_mode 1), or
+             * everybody (2).  A unit of human reads turns to the table after its first hit has come back;
+             * a unit that keeps missing pays one request per lookup instead of 1.65 */
+            const bool ask = sp.filter_mode == 2 || sm.groups[sm.owner[meta & 31u]] == 0u;
+            const uint32_t st = (uint32_t)idx & (ask ? 31u : 7u);
+            f_unit = (uint32_t)(idx >> (ask ? 5 : 3));
+            f_ckey = (uint32_t)(h >> (32u + db.value_bits)) | (st << ck_bits);
+            f_aux = ask ? (meta | NH_AUX_FILTER) : meta;
+          } else {
+            f_unit = (uint32_t)(idx >> 3);
+            f_start = (uint32_t)idx & 7u;
+            f_ckey = (uint32_t)(h >> (32u + db.value_bits));
+            f_aux = meta; /* zero sectors visited */
+          }
         }
       }
       cq_n = 0;
@@ -1160,8 +1280,14 @@ k_stream_classify(const NhDbParams db, const NhBatchPtrs b, const NhScoreParams 
         const uint32_t u0 = __shfl_sync(FULL_MASK, mine, src_lane);
         const uint32_t u1 = __shfl_sync(FULL_MASK, mine, 16u + src_lane);
         const uint32_t dst = sect0 + src_lane * 32u + half * 16u;
-        if (u0 != 0xFFFFFFFFu) cp_async16_l2_64(dst, db.cells + (uint64_t)u0 * 8ULL + half * 4u);
-        if (u1 != 0xFFFFFFFFu) cp_async16_l2_64(dst + 512u, db.cells + (uint64_t)u1 * 8ULL + half * 4u);
+        const uint32_t *src0 = db.cells, *src1 = db.cells;
+        if (FILTER) { /* filter records and table sectors are both 32 bytes, indexed alike */
+          const uint32_t fmask = __ballot_sync(FULL_MASK, f_aux != NH_AUX_NONE && (f_aux & NH_AUX_FILTER));
+          if ((fmask >> src_lane) & 1u) src0 = sp.filter;
+          if ((fmask >> (16u + src_lane)) & 1u) src1 = sp.filter;
+        }
+        if (u0 != 0xFFFFFFFFu) cp_async16_l2_64(dst, src0 + (uint64_t)u0 * 8ULL + half * 4u);
+        if (u1 != 0xFFFFFFFFu) cp_async16_l2_64(dst + 512u, src1 + (uint64_t)u1 * 8ULL + half * 4u);
         cp_async_arrive(sbar);
       }
       __syncwarp(); /* queue slots just read may be overwritten by the next pushes */
@@ -1657,18 +1783,24 @@ cudaError_t nh_kernels_init(void) {
 #define NH_SET_SMEM(kern, bytes)                                                             \
   e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);       \
   if (e != cudaSuccess) return e;
-  NH_SET_SMEM((k_stream_classify<5, 1, false, false, false, false>), smax)
-  NH_SET_SMEM((k_stream_classify<5, 1, false, false, true, false>), smax_emit)
-  NH_SET_SMEM((k_stream_classify<5, 0, false, false, false, false>), smax)
-  NH_SET_SMEM((k_stream_classify<5, 0, false, true, false, false>), smax)
-  NH_SET_SMEM((k_stream_classify<5, 0, true, false, false, false>), smax)
-  NH_SET_SMEM((k_stream_classify<5, 0, false, false, true, false>), smax_emit)
-  NH_SET_SMEM((k_stream_classify<5, 0, false, true, true, false>), smax_emit)
-  NH_SET_SMEM((k_stream_classify<5, 1, false, false, false, true>), smax)
-  NH_SET_SMEM((k_stream_classify<5, 0, false, false, false, true>), smax)
-  NH_SET_SMEM((k_stream_classify<5, 0, false, true, false, true>), smax)
+  NH_SET_SMEM((k_stream_classify<5, 1, false, false, false, false, false>), smax)
+  NH_SET_SMEM((k_stream_classify<5, 1, false, false, true, false, false>), smax_emit)
+  NH_SET_SMEM((k_stream_classify<5, 0, false, false, false, false, false>), smax)
+  NH_SET_SMEM((k_stream_classify<5, 0, false, true, false, false, false>), smax)
+  NH_SET_SMEM((k_stream_classify<5, 0, true, false, false, false, false>), smax)
+  NH_SET_SMEM((k_stream_classify<5, 0, false, false, true, false, false>), smax_emit)
+  NH_SET_SMEM((k_stream_classify<5, 0, false, true, true, false, false>), smax_emit)
+  NH_SET_SMEM((k_stream_classify<5, 1, false, false, false, true, false>), smax)
+  NH_SET_SMEM((k_stream_classify<5, 0, false, false, false, true, false>), smax)
+  NH_SET_SMEM((k_stream_classify<5, 0, false, true, false, true, false>), smax)
+  NH_SET_SMEM((k_stream_classify<5, 1, false, false, false, false, true>), smax)
+  NH_SET_SMEM((k_stream_classify<5, 1, false, false, false, true, true>), smax)
 #undef NH_SET_SMEM
   return cudaSuccess;
+}
+
+void nh_launch_filter_build(const NhDbParams &db, uint32_t *filter, uint32_t n_blocks, cudaStream_t st) {
+  k_filter_build<<<(n_blocks + 255u) / 256u, 256, 0, st>>>(db.cells, db.capacity, db.value_bits, db.value_mask, filter, n_blocks);
 }
 
 int nh_launch_len_scan(const uint32_t *len, uint32_t n_seqs, uint64_t *sums, uint64_t *off, uint32_t *poff, cudaStream_t st) {
@@ -1712,8 +1844,14 @@ int nh_launch_stream(const NhDbParams &db, const NhBatchPtrs &b, const NhScorePa
    * constants compiled in; anything else with a window of 5 takes the generic one */
   const bool kl_default = db.k == 35 && db.l == 31 && db.revcom_version != 0;
 #define NH_LAUNCH(KLv, DBGv, REVv, EMITv, PACKv) \
-  k_stream_classify<5, KLv, DBGv, REVv, EMITv, PACKv><<<grid, NH_BLOCK_THREADS, smem, st>>>(db, b, sp)
-  if (b.codes != nullptr) { /* packed input: never with the per-position debug output or per-read runs */
+  k_stream_classify<5, KLv, DBGv, REVv, EMITv, PACKv, false><<<grid, NH_BLOCK_THREADS, smem, st>>>(db, b, sp)
+#define NH_LAUNCH_FILTER(PACKv) \
+  k_stream_classify<5, 1, false, false, false, PACKv, true><<<grid, NH_BLOCK_THREADS, smem, st>>>(db, b, sp)
+  /* the miss filter goes with the default instantiations (k 35, l 31, no per-read output) */
+  const bool filter = sp.filter != nullptr && sp.filter_mode != 0 && kl_default && !emit && b.dbg_pos_min == nullptr;
+  if (filter && b.codes != nullptr) NH_LAUNCH_FILTER(true);
+  else if (filter) NH_LAUNCH_FILTER(false);
+  else if (b.codes != nullptr) { /* packed input: never with the per-position debug output or per-read runs */
     if (kl_default) NH_LAUNCH(1, false, false, false, true);
     else if (db.revcom_version == 0) NH_LAUNCH(0, false, true, false, true);
     else NH_LAUNCH(0, false, false, false, true);
@@ -1726,6 +1864,7 @@ int nh_launch_stream(const NhDbParams &db, const NhBatchPtrs &b, const NhScorePa
   else if (emit) NH_LAUNCH(0, false, false, true, false);
   else NH_LAUNCH(0, false, false, false, false);
 #undef NH_LAUNCH
+#undef NH_LAUNCH_FILTER
   return 1;
 }
 

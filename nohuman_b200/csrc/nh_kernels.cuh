@@ -146,11 +146,19 @@ struct NhScoreParams {
   int32_t min_hit_groups;
   int32_t keep_human;
   int32_t lane_taxa;   /* fused kernel: taxon slots per unit before it overflows (<= NH_LANE_TAXA) */
+  int32_t filter_mode; /* fused kernel: 0 never ask the miss filter, 1 units without a hit so far ask it first, 2 every lookup does */
+  /* the miss filter (nh_kernels.cu, k_filter_build): one 32-byte record per block of 32 cells, or null.  It lives
+   * here, in the LAST kernel parameter, on purpose: growing NhDbParams by these 16 bytes made ptxas rematerialise
+   * addresses all over k_stream_classify (2496 -> 2616 SASS instructions, +12 % executed) */
+  const uint32_t *filter;
+  uint32_t n_filter_blocks;
 };
 
 /* launchers (nh_kernels.cu); each returns the number of kernels launched */
 int nh_launch_plan(const NhDbParams &db, const NhBatchPtrs &b, cudaStream_t st);
 /* sequence lengths -> base offsets and first units (sums: 2 * ceil(n_seqs / 1024) words of scratch); returns the launches */
+/* builds the miss filter of db.cells: n_blocks = ceil(capacity / 32) records of 32 bytes */
+void nh_launch_filter_build(const NhDbParams &db, uint32_t *filter, uint32_t n_blocks, cudaStream_t st);
 int nh_launch_len_scan(const uint32_t *len, uint32_t n_seqs, uint64_t *sums, uint64_t *off, uint32_t *poff, cudaStream_t st);
 /* streaming path: lane-serial minimizer scan feeding the probe, in-warp scoring */
 bool nh_fused_supported(const NhDbParams &db);

@@ -206,6 +206,11 @@ extern "C" int nh_synth_build_db(const void *opts, size_t opts_len, const void *
   }
   db->info.size = size;
   if (genome_bases) *genome_bases = gpos + (k - 1);
+  rc = nh_db_build_filter(db);
+  if (rc) {
+    nh_db_close(db);
+    return rc;
+  }
   *out = db;
   return NH_OK;
 }

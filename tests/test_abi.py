@@ -47,7 +47,7 @@ def test_binding_table_covers_the_header(nh):
 
 def test_abi_version_and_struct_sizes(nh):
     L = nh.lib()
-    assert L.nh_abi_version() == 2
+    assert L.nh_abi_version() == 3
     # struct layouts the ctypes mirror must agree with (sizes asserted against the C compiler)
     prog = r'''
 #include <stdio.h>

@@ -113,3 +113,36 @@ def test_read_hitting_more_taxa_than_any_shared_table(oracle, tmp_path):
         np.testing.assert_array_equal(tk, want["total_kmers"])
         np.testing.assert_array_equal(call, want["ext"])
     assert want["hit_groups"][0] > 16_384
+
+
+@pytest.mark.parametrize("name,load,cap_adjust", [
+    ("load_0.95", 0.95, 0),        # long probe chains: filter records whose block has no free cell left
+    ("load_0.99_odd", 0.99, 13),   # capacity not a multiple of 32 (and of 8): partial last block and sector
+    ("load_0.5_prime", 0.5, -1),   # cap_adjust -1: the next prime, nothing divides it
+])
+@pytest.mark.parametrize("filter_mode", ["1", "2", "0"])
+def test_miss_filter_on_awkward_tables(oracle, tmp_path, name, load, cap_adjust, filter_mode, monkeypatch):
+    """The miss filter (one record per block of 32 cells: occupancy + Bloom bits) must never change a call:
+    tables so full that chains run through several blocks, capacities with a partial last block, every
+    policy (0 never asked, 1 units without a hit so far, 2 every lookup)."""
+    monkeypatch.setenv("NH_FILTER_MODE", filter_mode)
+    genomes = synth.cfg1_genomes(seed=5, scale=0.004)
+    tax = [oracle.TaxSpec(*t) for t in synth.TAXONOMY_CFG1]
+    probe = oracle.OracleDb.build([(t, bytes(g)) for t, g in genomes], tax, load_factor=load)
+    cap = int(probe.cht.capacity)
+    if cap_adjust == -1:
+        cap |= 1
+        while any(cap % p == 0 for p in range(3, 2000, 2)):
+            cap += 2
+    else:
+        cap += cap_adjust
+    db = oracle.OracleDb.build([(t, bytes(g)) for t, g in genomes], tax, capacity=cap)
+    d = str(tmp_path / name)
+    db.save(d)
+    db.genomes = genomes
+    from nohuman_b200 import Database
+    with Database.open(d, 0) as gdb:
+        assert (gdb.info.filter_bytes > 0) == True
+        assert gdb.info.filter_bytes == (cap + 31) // 32 * 32
+    check(db, d, True, paired=True, conf=0.1)
+    check(db, d, True, paired=False, conf=0.0)

@@ -118,14 +118,19 @@ def test_edge_cases(small_db, gpu_db):
         _compare_batch(small_db, sess, pseqs, True, 0.2)
 
 
-@pytest.mark.parametrize("mode", ["legacy", "lane_taxa_1", "lane_taxa_2", "tile_pos_60", "tile_pos_256", "tile_pos_1023"])
+@pytest.mark.parametrize("mode", ["legacy", "lane_taxa_1", "lane_taxa_2", "tile_pos_60", "tile_pos_256", "tile_pos_1023",
+                                  "filter_mode_0", "filter_mode_2"])
 def test_kernel_path_variants_match_oracle(small_db, gpu_db, mode, monkeypatch):
     """The warp-per-tile kernels (NH_LEGACY_KERNELS=1), the streaming kernel with a shrunken
     in-warp taxon table (units overflow into k_score_big, which classifies them again from
-    their bases) and other tile sizes give the answers of the default path and of the oracle."""
+    their bases), other tile sizes and the other two policies for the miss filter give the
+    answers of the default path and of the oracle."""
     from nohuman_b200 import Session
     if mode == "legacy":
         monkeypatch.setenv("NH_LEGACY_KERNELS", "1")
+    elif mode.startswith("filter_mode"):
+        # the miss filter: never asked / asked by every lookup (default: by units without a hit so far)
+        monkeypatch.setenv("NH_FILTER_MODE", mode[-1])
     elif mode.startswith("tile_pos"):
         monkeypatch.setenv("NH_FUSED_TILE_POS", mode.split("_")[-1])  # 60: every 150 bp read becomes a multi-tile unit
     else:
