@@ -486,7 +486,10 @@ def main():
                     "window (perfect page locality; a hash table cannot produce it); uniform_random_* = best over the patterns "
                     "with uniformly random addresses, which is what hashing k-mers produces - the fused kernel runs at that "
                     "rate (a fraction slightly above 1 is the spread between a continuous microbenchmark and the kernel's "
-                    "bursts of 32 requests per warp)",
+                    "bursts of 32 requests per warp).  sectors_per_lookup counts every 32-byte request of the kernel, table "
+                    "sectors and miss-filter records alike: with the filter a lookup needs fewer of them than the table's "
+                    "probe chains alone (cpu_baseline.oracle_sectors_per_lookup), and the patterns are run at the kernel's "
+                    "own continuation rate",
         }
 
     # ---------------- parity: every rank, its own replica, one common batch ----------------

@@ -31,7 +31,7 @@ marks = [
     ("probe round 2: pop 32 lookups, fmix64 + hash % capacity, request the sectors (cp.async)", find("/* ---- 2. next 32 lookups", k0)),
     ("scan setup (tile geometry)", find("/* ---------------- scan, feeding the probe", k0)),
     ("emit: ballot / popc compaction of closed runs into the queue", find("auto emit = [&]", k0)),
-    ("scan: 2-bit codes, rolling l-mers, canonical, window minimum, run logic (per base)", find("auto scan_word = [&]", k0)),
+    ("scan: 2-bit codes, rolling l-mers, canonical, window minimum, run logic (per base)", find("auto scan_quad = [&]", k0)),
     ("base staging (cp.async chunks, mbarrier) and word loop", find("/* the lane's window for chunk c", k0)),
     ("drain, tile borders, deferred-tile hand-off", find("const bool has_runs", k0)),
     ("in-warp ResolveTree + keep/drop (leader lanes)", find("/* ---------------- score the units that live in this warp", k0)),
