@@ -576,10 +576,10 @@ def main():
         "run": {"table_load": round(hdr[1] / capacity, 4), "genome_bases": int(sdb.genome_bases),
                 "db_build_s": round(t_build, 2), "db_broadcast_s": round(t_bcast, 2),
                 "parallelism": f"dp{world} (read batches sharded, table replicated via NCCL broadcast)",
-                "miss_filter": {"bytes": int(db.info.filter_bytes), "mode": int(os.environ.get("NH_FILTER_MODE", "1")),
+                "miss_filter": {"bytes": int(db.info.filter_bytes), "mode": int(os.environ.get("NH_FILTER_MODE", "3")),
                                 "what": "one 32-byte record per block of 32 table cells (occupancy + Bloom bits of the keys stored "
-                                        "in the block), built on the device when the table is opened; units without a hit so far "
-                                        "ask it before the table, so a lookup that misses costs one request instead of 1.65 "
+                                        "in the block), built on the device when the table is opened; units whose last lookups "
+                                        "all missed ask it before the table, so a lookup that misses costs one request instead of 1.65 "
                                         "(DESIGN.md §2)"}},
         "reads_per_s": round(reads_s, 1),
         "stage_ms_per_launch": {k_: round(v, 4) for k_, v in stage.items()},

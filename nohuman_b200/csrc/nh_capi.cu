@@ -675,11 +675,11 @@ int nh_session_create_ex(nh_db *db, const nh_params_t *params, bool need_lookups
     const char *lt = getenv("NH_TEST_LANE_TAXA");
     int v = lt ? atoi(lt) : NH_LANE_TAXA;
     s->lane_taxa = v < 1 ? 1 : (v > NH_LANE_TAXA ? NH_LANE_TAXA : v);
-    /* NH_FILTER_MODE: 0 the streaming kernel never asks the miss filter, 1 (default) units without a hit so far ask
-     * it before the table, 2 every lookup does */
+    /* NH_FILTER_MODE — who asks the miss filter before the table: 0 nobody, 1 units none of whose lookups has hit so
+     * far, 2 every lookup, 3 (default) units whose last few lookups all missed */
     const char *fm = getenv("NH_FILTER_MODE");
-    s->filter_mode = fm ? atoi(fm) : 1;
-    if (s->filter_mode < 0 || s->filter_mode > 2) s->filter_mode = 1;
+    s->filter_mode = fm ? atoi(fm) : 3;
+    if (s->filter_mode < 0 || s->filter_mode > 3) s->filter_mode = 3;
     /* NH_FUSED_TILE_POS=n fixes the tile size of the streaming kernel (default: by mean read length) */
     const char *tp = getenv("NH_FUSED_TILE_POS");
     s->forced_tile_pos = tp ? atoi(tp) : 0;

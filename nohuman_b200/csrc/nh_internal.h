@@ -78,7 +78,7 @@ struct nh_session {
   uint64_t last_seqs = 0;
   bool use_fused = false, last_fused = false;
   int lane_taxa = NH_LANE_TAXA;
-  int filter_mode = 1;
+  int filter_mode = 3;
   int last_form = 0;       /* 0: warp-per-tile kernels, 2: k_stream_classify */
   int forced_tile_pos = 0; /* NH_FUSED_TILE_POS */
   NhTileTab *d_tile_tab = nullptr;

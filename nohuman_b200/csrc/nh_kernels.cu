@@ -870,6 +870,9 @@ k_score_big(const NhDbParams db, const NhBatchPtrs b, const NhScoreParams sp) {
 #endif
 #define NH_META_FIRST 0x8000u /* the first lookup of its tile */
 #define NH_AUX_NONE 0xFFFFFFFFu
+#ifndef NH_FILTER_RECENT
+#define NH_FILTER_RECENT 4u
+#endif
 #define NH_AUX_FILTER 0x80000000u /* FILTER kernels: the request in flight is a filter record, not a table sector */
 
 template <bool EMIT>
@@ -892,6 +895,7 @@ struct __align__(16) StreamWarpSmem {
   __align__(16) uint8_t bchunk[2][32 * NH_BCHUNK_STRIDE];
   __align__(16) uint32_t sect[32 * 8];
   uint32_t q_slot[EMIT ? 32 : 1]; /* per-read output only: where the lookup's taxon goes */
+  uint8_t recent[32];             /* FILTER kernels, per owner lane: lookups still to send straight to the table after a hit */
 };
 
 /* 3 blocks of 8 warps per SM (up to 85 registers): the overlap of table latency and scan happens
@@ -1097,6 +1101,7 @@ k_stream_classify(const NhDbParams db, const NhBatchPtrs b, const NhScoreParams 
       sm.cnts[i * 32 + lane] = 0;
     }
     sm.groups[lane] = 0;
+    if (FILTER) sm.recent[lane] = 0;
     sm.owner[lane] = (uint8_t)owner;
     if (lane == 0) {
       sm.overflow = 0;
@@ -1209,6 +1214,15 @@ k_stream_classify(const NhDbParams db, const NhBatchPtrs b, const NhScoreParams 
         if (active && done) {
           const uint32_t tile_lane = f_aux & 31u;
           if (EMIT) b.lk_taxon[f_slot] = result;
+          if (FILTER && sp.filter_mode == 3) {
+            /* hits come in bursts (an error-free stretch of a read): after a hit the unit's next NH_FILTER_RECENT
+             * lookups go straight to the table, after that many misses in a row it asks the filter again.
+             * Plain loads and stores: a lost update only changes who asks, never a result */
+            const uint32_t own = sm.owner[tile_lane];
+            const uint32_t r = sm.recent[own];
+            if (result) sm.recent[own] = NH_FILTER_RECENT;
+            else if (r) sm.recent[own] = (uint8_t)(r - 1u);
+          }
           if (result) {
             const uint32_t own = sm.owner[tile_lane];
             const uint32_t n = (f_aux >> 5) & 0x3FFu;
@@ -1249,10 +1263,11 @@ k_stream_classify(const NhDbParams db, const NhBatchPtrs b, const NhScoreParams 
         } else {
           const uint64_t idx = nh_fastmod(h, db.capacity, db.mod_m, db.mod_sh1, db.mod_sh2);
           if (FILTER) {
-            /* who asks the filter first: units none of whose lookups has hit so far (sp.filter_mode 1), or
-             * everybody (2).  A unit of human reads turns to the table after its first hit has come back;
-             * a unit that keeps missing pays one request per lookup instead of 1.65 */
-            const bool ask = sp.filter_mode == 2 || sm.groups[sm.owner[meta & 31u]] == 0u;
+            /* who asks the filter first: units whose last few lookups all missed (sp.filter_mode 3), units none of
+             * whose lookups has hit so far (1), or everybody (2).  A unit of human reads goes straight to the table
+             * while its hits keep coming; a unit that keeps missing pays one request per lookup instead of 1.65 */
+            const uint32_t own = sm.owner[meta & 31u];
+            const bool ask = sp.filter_mode == 2 || (sp.filter_mode == 3 ? sm.recent[own] == 0u : sm.groups[own] == 0u);
             const uint32_t st = (uint32_t)idx & (ask ? 31u : 7u);
             f_unit = (uint32_t)(idx >> (ask ? 5 : 3));
             f_ckey = (uint32_t)(h >> (32u + db.value_bits)) | (st << ck_bits);

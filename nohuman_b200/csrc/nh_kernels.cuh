@@ -146,7 +146,8 @@ struct NhScoreParams {
   int32_t min_hit_groups;
   int32_t keep_human;
   int32_t lane_taxa;   /* fused kernel: taxon slots per unit before it overflows (<= NH_LANE_TAXA) */
-  int32_t filter_mode; /* fused kernel: 0 never ask the miss filter, 1 units without a hit so far ask it first, 2 every lookup does */
+  int32_t filter_mode; /* fused kernel, who asks the miss filter before the table: 0 nobody, 1 units without a hit so far,
+                        * 2 every lookup, 3 units whose last NH_FILTER_RECENT lookups all missed */
   /* the miss filter (nh_kernels.cu, k_filter_build): one 32-byte record per block of 32 cells, or null.  It lives
    * here, in the LAST kernel parameter, on purpose: growing NhDbParams by these 16 bytes made ptxas rematerialise
    * addresses all over k_stream_classify (2496 -> 2616 SASS instructions, +12 % executed) */

@@ -120,11 +120,11 @@ def test_read_hitting_more_taxa_than_any_shared_table(oracle, tmp_path):
     ("load_0.99_odd", 0.99, 13),   # capacity not a multiple of 32 (and of 8): partial last block and sector
     ("load_0.5_prime", 0.5, -1),   # cap_adjust -1: the next prime, nothing divides it
 ])
-@pytest.mark.parametrize("filter_mode", ["1", "2", "0"])
+@pytest.mark.parametrize("filter_mode", ["1", "2", "3", "0"])
 def test_miss_filter_on_awkward_tables(oracle, tmp_path, name, load, cap_adjust, filter_mode, monkeypatch):
     """The miss filter (one record per block of 32 cells: occupancy + Bloom bits) must never change a call:
     tables so full that chains run through several blocks, capacities with a partial last block, every
-    policy (0 never asked, 1 units without a hit so far, 2 every lookup)."""
+    policy (0 never asked, 1 units without a hit so far, 2 every lookup, 3 units whose last lookups missed)."""
     monkeypatch.setenv("NH_FILTER_MODE", filter_mode)
     genomes = synth.cfg1_genomes(seed=5, scale=0.004)
     tax = [oracle.TaxSpec(*t) for t in synth.TAXONOMY_CFG1]

@@ -119,7 +119,7 @@ def test_edge_cases(small_db, gpu_db):
 
 
 @pytest.mark.parametrize("mode", ["legacy", "lane_taxa_1", "lane_taxa_2", "tile_pos_60", "tile_pos_256", "tile_pos_1023",
-                                  "filter_mode_0", "filter_mode_2"])
+                                  "filter_mode_0", "filter_mode_2", "filter_mode_3"])
 def test_kernel_path_variants_match_oracle(small_db, gpu_db, mode, monkeypatch):
     """The warp-per-tile kernels (NH_LEGACY_KERNELS=1), the streaming kernel with a shrunken
     in-warp taxon table (units overflow into k_score_big, which classifies them again from
@@ -129,7 +129,7 @@ def test_kernel_path_variants_match_oracle(small_db, gpu_db, mode, monkeypatch):
     if mode == "legacy":
         monkeypatch.setenv("NH_LEGACY_KERNELS", "1")
     elif mode.startswith("filter_mode"):
-        # the miss filter: never asked / asked by every lookup (default: by units without a hit so far)
+        # the miss filter: never asked / asked by every lookup / by units whose last few lookups missed (default: by units without a hit so far)
         monkeypatch.setenv("NH_FILTER_MODE", mode[-1])
     elif mode.startswith("tile_pos"):
         monkeypatch.setenv("NH_FUSED_TILE_POS", mode.split("_")[-1])  # 60: every 150 bp read becomes a multi-tile unit
