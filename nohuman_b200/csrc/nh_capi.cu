@@ -691,6 +691,8 @@ int nh_session_create_ex(nh_db *db, const nh_params_t *params, bool need_lookups
   /* every sequence has at most ceil(positions / tile_pos) tiles; sized for the smallest tile any
    * kernel of this session may use */
   int min_tile = db->params.tile_pos < NH_FUSED_TILE_POS_LONG ? db->params.tile_pos : NH_FUSED_TILE_POS_LONG;
+  /* packed input rounds a forced tile size down to a multiple of 32 (enqueue_batch): size for that */
+  if (s->forced_tile_pos) min_tile = std::min(min_tile, std::max(32, s->forced_tile_pos & ~31));
   if (s->forced_tile_pos && s->forced_tile_pos < min_tile) min_tile = s->forced_tile_pos;
   if (!s->use_fused || need_lookups) min_tile = std::min(min_tile, (int)db->params.tile_pos);
   s->cap_tiles = ms + mb / (uint64_t)min_tile + 1;
@@ -870,6 +872,9 @@ static int enqueue_batch(nh_session *s, const uint8_t *d_bases, const uint64_t *
   SP.n_filter_blocks = s->db->n_filter_blocks;
   const int sm = s->db->sm_count;
   uint64_t tiles_upper = n_seqs + total_bases / (uint64_t)P.tile_pos + 1;
+  if (tiles_upper > s->cap_tiles) /* cannot happen for batches within the session's capacity; never write past the tile arrays */
+    return nh_set_error(NH_ERR_CAPACITY, "batch needs %llu tiles of %d positions, session holds %llu",
+                        (unsigned long long)tiles_upper, (int)P.tile_pos, (unsigned long long)s->cap_tiles);
   uint64_t lookups_upper = total_bases;
   int launches = 0;
   cudaStream_t st = s->stream;

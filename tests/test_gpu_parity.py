@@ -214,7 +214,7 @@ def test_repeated_minimizers_across_tile_borders(small_db, gpu_db, monkeypatch):
         _compare_batch(small_db, sess, seqs, False, 0.0)
 
 
-@pytest.mark.parametrize("mode", ["default", "lane_taxa_1", "tile_pos_96"])
+@pytest.mark.parametrize("mode", ["default", "lane_taxa_1", "tile_pos_96", "tile_pos_33"])
 def test_packed_input_matches_ascii_and_oracle(small_db, gpu_db, mode, monkeypatch):
     """nh_classify_batch_packed (2-bit codes + validity bits packed on the host): same per-unit call, k-mer
     total and hit groups as the ASCII entry point and the oracle - ragged lengths, N runs, lower case, junk
@@ -223,8 +223,10 @@ def test_packed_input_matches_ascii_and_oracle(small_db, gpu_db, mode, monkeypat
     from nohuman_b200 import Session
     if mode == "lane_taxa_1":
         monkeypatch.setenv("NH_TEST_LANE_TAXA", "1")
-    if mode == "tile_pos_96":
-        monkeypatch.setenv("NH_FUSED_TILE_POS", "96")
+    if mode.startswith("tile_pos"):
+        # 33: packed input rounds the tile size down to 32, so the batch has more tiles than the ASCII path
+        # would cut (the tile arrays were once sized for 33: tools/fuzz_parity.py found the overrun)
+        monkeypatch.setenv("NH_FUSED_TILE_POS", mode.split("_")[-1])
     rng = np.random.default_rng(23)
     g = dict(small_db.genomes)
     seqs = synth.illumina_reads(small_db.genomes, 1200, 150, seed=12, paired=True, n_rate=0.2)

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Randomised parity hunt: many small batches of odd shapes (lengths 0..20 kb around every tile / group border,
-N runs, lower case, junk bytes, paired and single, random --conf, random tile sizes, shrunken taxon tables) through
-the C ABI against the CPU oracle on the cfg1-shaped database.  Prints the first mismatch with a reproducer seed.
+N runs, lower case, junk bytes, paired and single, random --conf, random tile sizes, shrunken taxon tables, every
+policy of the miss filter, ASCII and packed transfer) through the C ABI against the CPU oracle on the cfg1-shaped database.  Prints the first mismatch with a reproducer seed.
 
     python tools/fuzz_parity.py [--seconds 120] [--seed 1]
 """
@@ -41,6 +41,8 @@ def main():
         rng = np.random.default_rng(seed)
         tile_pos = int(rng.choice([0, 0, 16, 33, 60, 100, 252, 508, 511, 1023]))
         lane_taxa = int(rng.choice([8, 8, 8, 1, 2, 3]))
+        filter_mode = int(rng.choice([3, 3, 0, 1, 2]))   # who asks the miss filter
+        entry = str(rng.choice(["ascii", "ascii", "pack"]))  # nh_classify_batch / nh_classify_batch_pack
         paired = bool(rng.integers(0, 2))
         conf = float(rng.choice([0.0, 0.01, 0.1, 0.25, 0.5, 0.9, 1.0]))
         keep_human = bool(rng.integers(0, 2))
@@ -89,18 +91,26 @@ def main():
         else:
             os.environ.pop("NH_FUSED_TILE_POS", None)
         os.environ["NH_TEST_LANE_TAXA"] = str(lane_taxa)
+        os.environ["NH_FILTER_MODE"] = str(filter_mode)
         odb.confidence = conf
         want = odb.classify_batch(bases, offsets, paired=paired)
+        if os.environ.get("NH_FUZZ_VERBOSE"):
+            print(f"it={it} seed={seed} tile_pos={tile_pos} lane_taxa={lane_taxa} filter_mode={filter_mode} entry={entry} paired={paired} "
+                  f"conf={conf} n_seqs={len(seqs)} bases={len(bases)}", flush=True)
         with Database.open(d, 0) as db, Session(db, confidence=conf, paired=paired, keep_human=keep_human,
                                                 max_batch_bases=len(bases) + 4096, max_batch_seqs=len(seqs) + 2) as sess:
-            call, keep, st = sess.classify(bases, offsets)
+            if entry == "pack":
+                call, keep, st = sess.classify_pack(bases, offsets, threads=int(rng.integers(1, 7)))
+            else:
+                call, keep, st = sess.classify(bases, offsets)
             icall, tk, hg = sess.debug_last_batch(len(call))
         cls = (want["ext"] != 0).astype(np.uint8)
         ok = (np.array_equal(call, want["ext"]) and np.array_equal(tk, want["total_kmers"]) and np.array_equal(hg, want["hit_groups"])
               and np.array_equal(keep, cls if keep_human else 1 - cls))
         if not ok:
             bad = np.nonzero((call != want["ext"]) | (tk != want["total_kmers"]) | (hg != want["hit_groups"]))[0]
-            print(f"MISMATCH seed={seed} it={it} tile_pos={tile_pos} lane_taxa={lane_taxa} paired={paired} conf={conf} units={bad[:10].tolist()}")
+            print(f"MISMATCH seed={seed} it={it} tile_pos={tile_pos} lane_taxa={lane_taxa} filter_mode={filter_mode} entry={entry} "
+                  f"paired={paired} conf={conf} units={bad[:10].tolist()}")
             for u in bad[:3]:
                 nm = 2 if paired else 1
                 print("  unit", int(u), "lens", [int(offsets[u * nm + j + 1] - offsets[u * nm + j]) for j in range(nm)],
