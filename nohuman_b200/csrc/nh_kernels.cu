@@ -1028,7 +1028,8 @@ k_filter_build(const uint32_t *__restrict__ cells, uint64_t capacity, uint32_t v
  * immediates); KL = 0: any k, l with k - l + 1 = W, read from the database.
  * PACKED: the batch came as 2-bit codes + validity bits (nh_classify_batch_packed), every sequence
  * starting on a unit of 32 bases; tiles then start on units too (tile_pos is a multiple of 32). */
-template <int W, int KL, bool DBG, bool REV0, bool EMIT, bool PACKED, bool FILTER>
+/* FILTER: 0 no miss filter, 1 / 2 / 3 the policy of NhScoreParams::filter_mode compiled in */
+template <int W, int KL, bool DBG, bool REV0, bool EMIT, bool PACKED, int FILTER>
 __global__ void __launch_bounds__(NH_BLOCK_THREADS, NH_STREAM_MIN_BLOCKS)
 k_stream_classify(const NhDbParams db, const NhBatchPtrs b, const NhScoreParams sp) {
   static_assert(W == 5, "the scan consumes one 4-byte word per ring rotation");
@@ -1101,7 +1102,7 @@ k_stream_classify(const NhDbParams db, const NhBatchPtrs b, const NhScoreParams 
       sm.cnts[i * 32 + lane] = 0;
     }
     sm.groups[lane] = 0;
-    if (FILTER) sm.recent[lane] = 0;
+    if (FILTER == 3) sm.recent[lane] = 0;
     sm.owner[lane] = (uint8_t)owner;
     if (lane == 0) {
       sm.overflow = 0;
@@ -1214,7 +1215,7 @@ k_stream_classify(const NhDbParams db, const NhBatchPtrs b, const NhScoreParams 
         if (active && done) {
           const uint32_t tile_lane = f_aux & 31u;
           if (EMIT) b.lk_taxon[f_slot] = result;
-          if (FILTER && sp.filter_mode == 3) {
+          if (FILTER == 3) {
             /* hits come in bursts (an error-free stretch of a read): after a hit the unit's next NH_FILTER_RECENT
              * lookups go straight to the table, after that many misses in a row it asks the filter again.
              * Plain loads and stores: a lost update only changes who asks, never a result */
@@ -1267,7 +1268,7 @@ k_stream_classify(const NhDbParams db, const NhBatchPtrs b, const NhScoreParams 
              * whose lookups has hit so far (1), or everybody (2).  A unit of human reads goes straight to the table
              * while its hits keep coming; a unit that keeps missing pays one request per lookup instead of 1.65 */
             const uint32_t own = sm.owner[meta & 31u];
-            const bool ask = sp.filter_mode == 2 || (sp.filter_mode == 3 ? sm.recent[own] == 0u : sm.groups[own] == 0u);
+            const bool ask = FILTER == 2 || (FILTER == 3 ? sm.recent[own] == 0u : sm.groups[own] == 0u);
             const uint32_t st = (uint32_t)idx & (ask ? 31u : 7u);
             f_unit = (uint32_t)(idx >> (ask ? 5 : 3));
             f_ckey = (uint32_t)(h >> (32u + db.value_bits)) | (st << ck_bits);
@@ -1798,18 +1799,22 @@ cudaError_t nh_kernels_init(void) {
 #define NH_SET_SMEM(kern, bytes)                                                             \
   e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);       \
   if (e != cudaSuccess) return e;
-  NH_SET_SMEM((k_stream_classify<5, 1, false, false, false, false, false>), smax)
-  NH_SET_SMEM((k_stream_classify<5, 1, false, false, true, false, false>), smax_emit)
-  NH_SET_SMEM((k_stream_classify<5, 0, false, false, false, false, false>), smax)
-  NH_SET_SMEM((k_stream_classify<5, 0, false, true, false, false, false>), smax)
-  NH_SET_SMEM((k_stream_classify<5, 0, true, false, false, false, false>), smax)
-  NH_SET_SMEM((k_stream_classify<5, 0, false, false, true, false, false>), smax_emit)
-  NH_SET_SMEM((k_stream_classify<5, 0, false, true, true, false, false>), smax_emit)
-  NH_SET_SMEM((k_stream_classify<5, 1, false, false, false, true, false>), smax)
-  NH_SET_SMEM((k_stream_classify<5, 0, false, false, false, true, false>), smax)
-  NH_SET_SMEM((k_stream_classify<5, 0, false, true, false, true, false>), smax)
-  NH_SET_SMEM((k_stream_classify<5, 1, false, false, false, false, true>), smax)
-  NH_SET_SMEM((k_stream_classify<5, 1, false, false, false, true, true>), smax)
+  NH_SET_SMEM((k_stream_classify<5, 1, false, false, false, false, 0>), smax)
+  NH_SET_SMEM((k_stream_classify<5, 1, false, false, true, false, 0>), smax_emit)
+  NH_SET_SMEM((k_stream_classify<5, 0, false, false, false, false, 0>), smax)
+  NH_SET_SMEM((k_stream_classify<5, 0, false, true, false, false, 0>), smax)
+  NH_SET_SMEM((k_stream_classify<5, 0, true, false, false, false, 0>), smax)
+  NH_SET_SMEM((k_stream_classify<5, 0, false, false, true, false, 0>), smax_emit)
+  NH_SET_SMEM((k_stream_classify<5, 0, false, true, true, false, 0>), smax_emit)
+  NH_SET_SMEM((k_stream_classify<5, 1, false, false, false, true, 0>), smax)
+  NH_SET_SMEM((k_stream_classify<5, 0, false, false, false, true, 0>), smax)
+  NH_SET_SMEM((k_stream_classify<5, 0, false, true, false, true, 0>), smax)
+  NH_SET_SMEM((k_stream_classify<5, 1, false, false, false, false, 1>), smax)
+  NH_SET_SMEM((k_stream_classify<5, 1, false, false, false, false, 2>), smax)
+  NH_SET_SMEM((k_stream_classify<5, 1, false, false, false, false, 3>), smax)
+  NH_SET_SMEM((k_stream_classify<5, 1, false, false, false, true, 1>), smax)
+  NH_SET_SMEM((k_stream_classify<5, 1, false, false, false, true, 2>), smax)
+  NH_SET_SMEM((k_stream_classify<5, 1, false, false, false, true, 3>), smax)
 #undef NH_SET_SMEM
   return cudaSuccess;
 }
@@ -1859,13 +1864,20 @@ int nh_launch_stream(const NhDbParams &db, const NhBatchPtrs &b, const NhScorePa
    * constants compiled in; anything else with a window of 5 takes the generic one */
   const bool kl_default = db.k == 35 && db.l == 31 && db.revcom_version != 0;
 #define NH_LAUNCH(KLv, DBGv, REVv, EMITv, PACKv) \
-  k_stream_classify<5, KLv, DBGv, REVv, EMITv, PACKv, false><<<grid, NH_BLOCK_THREADS, smem, st>>>(db, b, sp)
-#define NH_LAUNCH_FILTER(PACKv) \
-  k_stream_classify<5, 1, false, false, false, PACKv, true><<<grid, NH_BLOCK_THREADS, smem, st>>>(db, b, sp)
+  k_stream_classify<5, KLv, DBGv, REVv, EMITv, PACKv, 0><<<grid, NH_BLOCK_THREADS, smem, st>>>(db, b, sp)
+#define NH_LAUNCH_FILTER(PACKv, POLv) \
+  k_stream_classify<5, 1, false, false, false, PACKv, POLv><<<grid, NH_BLOCK_THREADS, smem, st>>>(db, b, sp)
   /* the miss filter goes with the default instantiations (k 35, l 31, no per-read output) */
   const bool filter = sp.filter != nullptr && sp.filter_mode != 0 && kl_default && !emit && b.dbg_pos_min == nullptr;
-  if (filter && b.codes != nullptr) NH_LAUNCH_FILTER(true);
-  else if (filter) NH_LAUNCH_FILTER(false);
+  if (filter && b.codes != nullptr) {
+    if (sp.filter_mode == 1) NH_LAUNCH_FILTER(true, 1);
+    else if (sp.filter_mode == 2) NH_LAUNCH_FILTER(true, 2);
+    else NH_LAUNCH_FILTER(true, 3);
+  } else if (filter) {
+    if (sp.filter_mode == 1) NH_LAUNCH_FILTER(false, 1);
+    else if (sp.filter_mode == 2) NH_LAUNCH_FILTER(false, 2);
+    else NH_LAUNCH_FILTER(false, 3);
+  }
   else if (b.codes != nullptr) { /* packed input: never with the per-position debug output or per-read runs */
     if (kl_default) NH_LAUNCH(1, false, false, false, true);
     else if (db.revcom_version == 0) NH_LAUNCH(0, false, true, false, true);
