@@ -895,7 +895,7 @@ struct __align__(16) StreamWarpSmem {
   __align__(16) uint8_t bchunk[2][32 * NH_BCHUNK_STRIDE];
   __align__(16) uint32_t sect[32 * 8];
   uint32_t q_slot[EMIT ? 32 : 1]; /* per-read output only: where the lookup's taxon goes */
-  uint8_t recent[32];             /* FILTER kernels, per owner lane: lookups still to send straight to the table after a hit */
+  uint8_t recent[32];             /* FILTER kernels, per tile: lookups still to send straight to the table after a hit */
 };
 
 /* 3 blocks of 8 warps per SM (up to 85 registers): the overlap of table latency and scan happens
@@ -1216,13 +1216,12 @@ k_stream_classify(const NhDbParams db, const NhBatchPtrs b, const NhScoreParams 
           const uint32_t tile_lane = f_aux & 31u;
           if (EMIT) b.lk_taxon[f_slot] = result;
           if (FILTER == 3) {
-            /* hits come in bursts (an error-free stretch of a read): after a hit the unit's next NH_FILTER_RECENT
+            /* hits come in bursts (an error-free stretch of a read): after a hit the tile's next NH_FILTER_RECENT
              * lookups go straight to the table, after that many misses in a row it asks the filter again.
              * Plain loads and stores: a lost update only changes who asks, never a result */
-            const uint32_t own = sm.owner[tile_lane];
-            const uint32_t r = sm.recent[own];
-            if (result) sm.recent[own] = NH_FILTER_RECENT;
-            else if (r) sm.recent[own] = (uint8_t)(r - 1u);
+            const uint32_t r = sm.recent[tile_lane];
+            if (result) sm.recent[tile_lane] = NH_FILTER_RECENT;
+            else if (r) sm.recent[tile_lane] = (uint8_t)(r - 1u);
           }
           if (result) {
             const uint32_t own = sm.owner[tile_lane];
@@ -1267,8 +1266,7 @@ k_stream_classify(const NhDbParams db, const NhBatchPtrs b, const NhScoreParams 
             /* who asks the filter first: units whose last few lookups all missed (sp.filter_mode 3), units none of
              * whose lookups has hit so far (1), or everybody (2).  A unit of human reads goes straight to the table
              * while its hits keep coming; a unit that keeps missing pays one request per lookup instead of 1.65 */
-            const uint32_t own = sm.owner[meta & 31u];
-            const bool ask = FILTER == 2 || (FILTER == 3 ? sm.recent[own] == 0u : sm.groups[own] == 0u);
+            const bool ask = FILTER == 2 || (FILTER == 3 ? sm.recent[meta & 31u] == 0u : sm.groups[sm.owner[meta & 31u]] == 0u);
             const uint32_t st = (uint32_t)idx & (ask ? 31u : 7u);
             f_unit = (uint32_t)(idx >> (ask ? 5 : 3));
             f_ckey = (uint32_t)(h >> (32u + db.value_bits)) | (st << ck_bits);
