@@ -67,21 +67,19 @@ uint64_t k2o_spaced_seed_mask(int l, int spaces) {
 /* ------------------------------------------------------------------ */
 /* MinimizerScanner (mmscanner.{h,cc})                 */
 
-static uint8_t g_lookup[256];
-static int g_lookup_ready = 0;
-static void init_lookup(void) {
-  if (g_lookup_ready) return;
-  memset(g_lookup, 0xFF, sizeof g_lookup);
-  g_lookup['A'] = g_lookup['a'] = 0;
-  g_lookup['C'] = g_lookup['c'] = 1;
-  g_lookup['G'] = g_lookup['g'] = 2;
-  g_lookup['T'] = g_lookup['t'] = 3;
-  g_lookup_ready = 1;
-}
+/* A compile-time table: it used to be filled on first use, and k2o_classify_batch creates its scanners inside
+ * the OpenMP region — a second thread's memset could blank the table under a first thread that was already
+ * scanning (a handful of bases read as ambiguous in the first batch of a process: __graft_entry__.smoke() once
+ * saw the oracle count 4 lookups fewer than the GPU). */
+#pragma GCC diagnostic push
+#pragma GCC diagnostic ignored "-Woverride-init"
+static const uint8_t g_lookup[256] = {
+    [0 ... 255] = 0xFF, ['A'] = 0, ['a'] = 0, ['C'] = 1, ['c'] = 1, ['G'] = 2, ['g'] = 2, ['T'] = 3, ['t'] = 3,
+};
+#pragma GCC diagnostic pop
 
 int k2o_scanner_init(k2o_scanner *s, int64_t k, int64_t l, uint64_t spaced_seed_mask, int dna,
                      uint64_t toggle_mask, int revcom_version) {
-  init_lookup();
   memset(s, 0, sizeof *s);
   if (l > 31 || l < 1 || k < l) return -1;
   s->k = k;
